@@ -1,0 +1,143 @@
+"""Mint golden vectors by EXECUTING the reference (authoring container only).
+
+Imports ``/root/reference/resource-estimation/qrnn.py`` (never copied into this
+repo), runs it on torch CPU and writes small ``.npz`` fixtures to
+``tests/golden/``.  ``/root/reference`` does not exist on the GPU box, so tests
+only ever read the committed fixtures.  Re-run:  ``python oracle/make_golden.py``.
+
+Inputs and (except G1) weights are pure functions of integer seeds
+(``deeprest_b200.synth``), so fixtures hold outputs + checksums, not tensors.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference/resource-estimation")
+
+from qrnn import QuantileRNN  # noqa: E402  (the reference itself)
+from deeprest_b200 import layout, synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# name, M, B, T, F, weight source, weight scale, x kind
+CASES = [
+    ("g1_cfg1_torchinit", 2, 1, 64, 16, "torch", 1.0, "uniform"),   # BASELINE configs[0]
+    ("g2_small", 4, 8, 64, 16, "synth", 1.0, "uniform"),
+    ("g2b_small_diurnal", 4, 8, 64, 16, "synth", 1.0, "diurnal"),
+    ("g3_long", 2, 2, 1440, 64, "synth", 1.0, "diurnal"),           # configs[4] horizon
+    ("g4_saturating", 4, 8, 64, 16, "synth", 3.0, "diurnal"),       # "trained-like": saturating gates
+    ("g6_odd", 3, 5, 7, 5, "synth", 2.0, "uniform"),                 # ragged: odd M, tiny T, F not /4
+    ("g7_f64_wide", 6, 130, 24, 64, "synth", 1.5, "uniform"),        # B crosses a 128-row tile
+]
+WSEED, XSEED, YSEED = 11, 2021, 2022
+
+
+def build_model(M, F, src, scale, dtype=torch.float32):
+    torch.manual_seed(0)
+    model = QuantileRNN(input_size=F, num_metrics=M)
+    if src == "synth":
+        blob = synth.weights(WSEED, M, F, scale)
+        sd = {k: torch.from_numpy(np.ascontiguousarray(v))
+              for k, v in layout.state_dict_from_blob(blob, M, F).items()}
+        model.load_state_dict(sd)
+    else:
+        blob = layout.blob_from_state_dict(model.state_dict(), M, F)
+    return model.to(dtype), blob
+
+
+def run_fp64(model, x):
+    """Same module in double precision (error floor). qrnn.py:39 builds h0 with the
+    default dtype, so flip the default while it runs."""
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    try:
+        with torch.no_grad():
+            return model.double()(torch.from_numpy(x).double()).numpy()
+    finally:
+        torch.set_default_dtype(prev)
+        model.float()
+
+
+class ReplayDropout(torch.nn.Module):
+    """Stands in for ``model.dropout`` (qrnn.py:15,43): same arithmetic as
+    nn.Dropout(p) — ``x * mask / (1-p)`` — but with a supplied mask per call."""
+
+    def __init__(self, masks, p):
+        super().__init__()
+        self.masks, self.p, self.i = masks, p, 0
+
+    def forward(self, t):
+        m = self.masks[self.i]
+        self.i += 1
+        return t * (m / (1.0 - self.p))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    for name, M, B, T, F, src, scale, kind in CASES:
+        model, blob = build_model(M, F, src, scale)
+        model.eval()
+        x = synth.windows(XSEED, B, T, F, kind)
+        y = synth.labels(YSEED, B, T, M)
+        with torch.no_grad():
+            out = model(torch.from_numpy(x))
+            loss = model.quantile_loss(out, torch.from_numpy(y)).item()
+        out64 = run_fp64(model, x)
+        payload = dict(
+            M=M, B=B, T=T, F=F, wsrc=src, wscale=scale, wseed=WSEED, xseed=XSEED, yseed=YSEED,
+            xkind=kind, out=out.numpy().astype(np.float32), out64=out64.astype(np.float64),
+            loss=np.float32(loss), blob_sum=np.float64(blob.astype(np.float64).sum()),
+            x_sum=np.float64(x.astype(np.float64).sum()), torch_version=torch.__version__,
+        )
+        if src == "torch":
+            payload["blob"] = blob
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **payload)
+        print(f"{name}: out {out.shape} |out|max {np.abs(out.numpy()).max():.4f} "
+              f"fp32-fp64 {np.abs(out.numpy() - out64).max():.2e} loss {loss:.6f}")
+
+    # G5 — one full training step with a replayed dropout mask (estimate.py:67-74).
+    M, B, T, F = 2, 4, 16, 16
+    model, blob = build_model(M, F, "synth", 1.0)
+    model.train()
+    x = synth.windows(XSEED, B, T, F, "diurnal")
+    y = synth.labels(YSEED, B, T, M)
+    mask_np = (synth.uniform(77, M * B * T * 2 * layout.H) >= 0.5).astype(np.float32)
+    mask_np = mask_np.reshape(M, B, T, 2 * layout.H)
+    model.dropout = ReplayDropout([torch.from_numpy(m) for m in mask_np], 0.5)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)      # estimate.py:61
+    out = model(torch.from_numpy(x))
+    loss = model.quantile_loss(out, torch.from_numpy(y))
+    opt.zero_grad()
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    opt.step()
+    gblob = layout.blob_from_state_dict(grads, M, F)
+    wblob = layout.blob_from_state_dict(model.state_dict(), M, F)
+    np.savez_compressed(
+        os.path.join(OUT, "g5_train_step.npz"), M=M, B=B, T=T, F=F, wseed=WSEED, wscale=1.0,
+        xseed=XSEED, yseed=YSEED, xkind="diurnal", mask_seed=77, lr=np.float32(1e-3),
+        out=out.detach().numpy(), loss=np.float32(loss.item()), grads=gblob,
+        weights_after=wblob, blob_sum=np.float64(blob.astype(np.float64).sum()),
+        torch_version=torch.__version__)
+    print(f"g5_train_step: loss {loss.item():.6f} |grad|max {np.abs(gblob).max():.3e}")
+
+    # G8 — host-side helpers either side of the path (utils.py:4-5, qrnn.py:69-75).
+    sys.path.insert(0, "/root/reference/resource-estimation")
+    from utils import sliding_window
+    ts = synth.uniform(5, 40 * 3).reshape(40, 3).astype(np.float64) * 7.0 - 1.0
+    win = sliding_window(ts, 6)
+    nm, lo, hi = QuantileRNN.normalization_minmax(win.copy(), split=12)
+    np.savez_compressed(os.path.join(OUT, "g8_window_norm.npz"), ts=ts, window=6, split=12,
+                        win=win, norm=nm, lo=lo, hi=hi)
+    print("g8_window_norm:", win.shape, lo, hi)
+
+
+if __name__ == "__main__":
+    main()
