@@ -1,0 +1,13 @@
+"""deeprest_b200 — B200-native (sm_100a) implementation of the DeepRest resource-estimator
+hot path: the batched ``QuantileRNN`` forward (reference resource-estimation/qrnn.py).
+
+Public surface:
+  * ``QuantileRNN``       host mirror of the reference module, backed by libdeeprest_b200.so
+  * ``layout``            weight-blob layout (reference state_dict order)
+  * ``synth``             counter-based synthetic trace/weight generator
+The CUDA library is loaded lazily on first use and there is no CPU fallback.
+"""
+from . import layout, synth  # noqa: F401
+from .estimator import QuantileRNN, sliding_window  # noqa: F401
+
+__all__ = ["QuantileRNN", "sliding_window", "layout", "synth"]

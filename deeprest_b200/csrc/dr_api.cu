@@ -1,0 +1,325 @@
+// C-ABI layer of libdeeprest_b200.so (see include/deeprest_b200.h for the contract and the
+// reference interface each entry point replaces). No torch types, no exceptions across the ABI.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "dr_common.cuh"
+
+static thread_local std::string g_create_err;
+
+int dr_fail(dr_model* m, int code, const std::string& msg) {
+    if (m) m->err = msg; else g_create_err = msg;
+    return code;
+}
+int dr_cuda_fail(dr_model* m, cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    return dr_fail(m, e == cudaErrorMemoryAllocation ? DR_ENOMEM : DR_ECUDA, msg);
+}
+
+int dr_reserve(dr_model* m, void** ptr, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *ptr) return DR_OK;
+    if (*ptr) { DR_CUDA(m, cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
+    if (bytes == 0) bytes = 16;
+    DR_CUDA(m, cudaMalloc(ptr, bytes));
+    *cap = bytes;
+    return DR_OK;
+}
+
+static int check_handle(dr_model* m) { return m ? DR_OK : DR_EINVAL; }
+
+extern "C" {
+
+int dr_version(void) { return 100; }
+
+int dr_has_engine(int32_t engine) {
+    if (engine == DR_ENGINE_AUTO || engine == DR_ENGINE_FFMA) return 1;
+    if (engine == DR_ENGINE_TC) return dr_tc_built() ? 1 : 0;
+    return 0;
+}
+
+const char* dr_last_error(const dr_model* m) { return m ? m->err.c_str() : g_create_err.c_str(); }
+
+int dr_create(const dr_config* cfg, dr_model** out) {
+    if (!cfg || !out) return dr_fail(nullptr, DR_EINVAL, "dr_create: null argument");
+    *out = nullptr;
+    if (cfg->H != DR_H) return dr_fail(nullptr, DR_EUNSUPPORTED, "hidden_layer_size must be 128 (reference default, qrnn.py:7)");
+    if (cfg->Q != DR_Q) return dr_fail(nullptr, DR_EUNSUPPORTED, "exactly 3 quantiles supported (reference default, qrnn.py:8)");
+    if (cfg->F < 1) return dr_fail(nullptr, DR_EINVAL, "input_size must be >= 1");
+    if (cfg->M < 2) return dr_fail(nullptr, DR_EINVAL, "num_metrics must be >= 2 (the reference's forward stacks the M-1 other experts, qrnn.py:52)");
+    if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return dr_fail(nullptr, DR_EINVAL, "bad rank/world");
+    if (cfg->M % cfg->world) return dr_fail(nullptr, DR_EINVAL, "num_metrics must be divisible by world (equal expert shards)");
+    if (cfg->engine < DR_ENGINE_AUTO || cfg->engine > DR_ENGINE_TC) return dr_fail(nullptr, DR_EINVAL, "bad engine");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return dr_fail(nullptr, DR_ECUDA, std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return dr_fail(nullptr, DR_EINVAL, "bad device ordinal");
+    ce = cudaSetDevice(cfg->device);
+    if (ce != cudaSuccess) return dr_cuda_fail(nullptr, ce, "cudaSetDevice");
+    cudaDeviceProp prop;
+    ce = cudaGetDeviceProperties(&prop, cfg->device);
+    if (ce != cudaSuccess) return dr_cuda_fail(nullptr, ce, "cudaGetDeviceProperties");
+    if (prop.major != 10) return dr_fail(nullptr, DR_ECUDA, "libdeeprest_b200 is built for sm_100a (B200) only");
+
+    dr_model* m = new (std::nothrow) dr_model();
+    if (!m) return dr_fail(nullptr, DR_ENOMEM, "host allocation failed");
+    m->cfg = *cfg;
+    m->M_loc = cfg->M / cfg->world;
+    m->e_lo = cfg->rank * m->M_loc;
+    m->e_hi = m->e_lo + m->M_loc;
+    m->Fp = (cfg->F + DR_KC - 1) / DR_KC * DR_KC;
+    m->off = dr_blob_offsets(cfg->F);
+    m->loaded = false;
+    m->sm_count = prop.multiProcessorCount;
+    m->last_engine = "none";
+    m->launches = 0;
+    m->profile = false; m->prof_n = 0; m->ev = nullptr;
+    m->stream = nullptr; m->own_stream = nullptr;
+    m->d_blob = m->d_mask = m->d_wf = m->d_bias4 = m->d_ct = m->d_abar = m->d_hb = nullptr;
+    m->d_wtc = nullptr; m->wtc_bytes = 0;
+    m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0;
+    m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
+    m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
+
+    int rc = DR_OK;
+    auto alloc = [&](float** p, size_t n) {
+        if (rc != DR_OK) return;
+        cudaError_t e = cudaMalloc((void**)p, (n ? n : 4) * sizeof(float));
+        if (e != cudaSuccess) rc = dr_cuda_fail(nullptr, e, "cudaMalloc(weights)");
+    };
+    size_t Ml = (size_t)m->M_loc, KT = (size_t)m->Fp + DR_H;
+    ce = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) rc = dr_cuda_fail(nullptr, ce, "cudaStreamCreate");
+    m->stream = m->own_stream;
+    alloc(&m->d_blob, Ml * m->off.per_expert);
+    alloc(&m->d_mask, Ml * cfg->F);
+    alloc(&m->d_wf, Ml * 2 * 2 * KT * 3 * 64);
+    alloc(&m->d_bias4, Ml * 2 * 4 * DR_H);
+    alloc(&m->d_ct, Ml * 2 * DR_Q * DR_H);
+    alloc(&m->d_abar, Ml * DR_Q * DR_2H);
+    alloc(&m->d_hb, Ml * DR_Q);
+    alloc(&m->d_loss, 8);
+    if (rc != DR_OK) { std::string keep = g_create_err; dr_destroy(m); g_create_err = keep; return rc; }
+    *out = m;
+    return DR_OK;
+}
+
+void dr_destroy(dr_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->cfg.device);
+    if (m->own_stream) cudaStreamSynchronize(m->own_stream);
+    void* ptrs[] = {m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+                    m->d_xT, m->d_xtc, m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->ev) { for (int i = 0; i < 4 * DR_PROF_MAX; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
+    delete m;
+}
+
+int dr_set_stream(dr_model* m, void* cuda_stream, int32_t use_caller_stream) {
+    if (check_handle(m)) return DR_EINVAL;
+    m->stream = use_caller_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+    return DR_OK;
+}
+
+int dr_profile(dr_model* m, int32_t enable) {
+    if (check_handle(m)) return DR_EINVAL;
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    if (enable && !m->ev) {
+        m->ev = new (std::nothrow) cudaEvent_t[4 * DR_PROF_MAX]();
+        if (!m->ev) return dr_fail(m, DR_ENOMEM, "host allocation failed");
+        for (int i = 0; i < 4 * DR_PROF_MAX; ++i) DR_CUDA(m, cudaEventCreate(&m->ev[i]));
+    }
+    m->profile = enable != 0;
+    m->prof_n = 0;
+    return DR_OK;
+}
+
+int dr_profile_read(dr_model* m, int32_t* n_forwards, float* gru_ms_sum, float* head_ms_sum) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!m->ev) return dr_fail(m, DR_ESTATE, "dr_profile_read: profiling was never enabled");
+    float g = 0.f, h = 0.f;
+    for (int i = 0; i < m->prof_n; ++i) {
+        float a = 0.f, b = 0.f;
+        DR_CUDA(m, cudaEventSynchronize(m->ev[4 * i + 3]));
+        DR_CUDA(m, cudaEventElapsedTime(&a, m->ev[4 * i + 0], m->ev[4 * i + 1]));
+        DR_CUDA(m, cudaEventElapsedTime(&b, m->ev[4 * i + 2], m->ev[4 * i + 3]));
+        g += a; h += b;
+    }
+    if (n_forwards) *n_forwards = m->prof_n;
+    if (gru_ms_sum) *gru_ms_sum = g;
+    if (head_ms_sum) *head_ms_sum = h;
+    return DR_OK;
+}
+
+int dr_local_experts(const dr_model* m, int32_t* lo, int32_t* hi) {
+    if (!m || !lo || !hi) return DR_EINVAL;
+    *lo = m->e_lo; *hi = m->e_hi;
+    return DR_OK;
+}
+
+int64_t dr_launch_count(const dr_model* m) { return m ? m->launches : -1; }
+const char* dr_last_engine(const dr_model* m) { return m ? m->last_engine : "none"; }
+
+int dr_load_weights(dr_model* m, const float* blob, size_t n) {
+    if (check_handle(m)) return DR_EINVAL;
+    size_t pe = (size_t)m->off.per_expert;
+    if (!blob || n != pe * m->cfg.M)
+        return dr_fail(m, DR_EINVAL, "dr_load_weights: blob must hold M*per_expert floats (" + std::to_string(pe * m->cfg.M) + ")");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    DR_CUDA(m, cudaMemcpyAsync(m->d_blob, blob + (size_t)m->e_lo * pe, (size_t)m->M_loc * pe * sizeof(float),
+                               cudaMemcpyHostToDevice, m->stream));
+    int rc = dr_launch_prep(m);
+    if (rc != DR_OK) return rc;
+    rc = dr_tc_prep_weights(m);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));   // the caller's blob is not retained past return
+    m->loaded = true;
+    return DR_OK;
+}
+
+int dr_get_weights(dr_model* m, float* blob, size_t n) {
+    if (check_handle(m)) return DR_EINVAL;
+    size_t pe = (size_t)m->off.per_expert;
+    if (!blob || n != pe * m->cfg.M) return dr_fail(m, DR_EINVAL, "dr_get_weights: wrong blob size");
+    if (!m->loaded) return dr_fail(m, DR_ESTATE, "dr_get_weights before dr_load_weights");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    DR_CUDA(m, cudaMemcpyAsync(blob + (size_t)m->e_lo * pe, m->d_blob, (size_t)m->M_loc * pe * sizeof(float),
+                               cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+static int check_shape(dr_model* m, int B, int T) {
+    if (B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "B and T must be >= 1");
+    if ((long long)B * T > (1LL << 31) / DR_2H) return dr_fail(m, DR_EINVAL, "B*T too large for one call; split the batch");
+    if (!m->loaded) return dr_fail(m, DR_ESTATE, "forward before dr_load_weights");
+    return DR_OK;
+}
+
+int dr_forward_local_dev(dr_model* m, const float* x, int32_t B, int32_t T, float* S, float* out_local) {
+    if (check_handle(m)) return DR_EINVAL;
+    int rc = check_shape(m, B, T);
+    if (rc != DR_OK) return rc;
+    if (!x || !S || !out_local) return dr_fail(m, DR_EINVAL, "null device pointer");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    size_t R = (size_t)B * T;
+    DR_CUDA(m, cudaMemsetAsync(S, 0, R * DR_2H * sizeof(float), m->stream));
+    DR_CUDA(m, cudaMemsetAsync(out_local, 0, R * m->M_loc * DR_Q * sizeof(float), m->stream));
+    if (m->M_loc == 0) return DR_OK;
+
+    bool use_tc = (m->cfg.engine == DR_ENGINE_TC) || (m->cfg.engine == DR_ENGINE_AUTO && dr_tc_supported(m, B, T));
+    if (use_tc) {
+        if (!dr_tc_supported(m, B, T)) return dr_fail(m, DR_EUNSUPPORTED, "tcgen05 engine does not support this shape");
+        m->last_engine = "tcgen05";
+        return dr_launch_gru_tc(m, x, B, T, S, out_local);     // records its own profile events
+    }
+    int BT = 16 * dr_ffma_rows_per_thread(B);
+    int Bp = (B + BT - 1) / BT * BT;
+    rc = dr_reserve(m, (void**)&m->d_xT, &m->xT_cap, (size_t)T * m->Fp * Bp * sizeof(float));
+    if (rc != DR_OK) return rc;
+    rc = dr_launch_xT(m, x, B, T, Bp);
+    if (rc != DR_OK) return rc;
+    m->last_engine = "ffma";
+    cudaEvent_t* ev = dr_prof_slot(m);
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
+    rc = dr_launch_gru_ffma(m, B, T, Bp, S, out_local);
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
+    return rc;
+}
+
+int dr_forward_heads_dev(dr_model* m, const float* S, int32_t B, int32_t T, float* out_local) {
+    if (check_handle(m)) return DR_EINVAL;
+    int rc = check_shape(m, B, T);
+    if (rc != DR_OK) return rc;
+    if (!S || !out_local) return dr_fail(m, DR_EINVAL, "null device pointer");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    cudaEvent_t* ev = dr_prof_slot(m);
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[2], m->stream));
+    rc = dr_launch_heads(m, S, B, T, out_local);
+    if (ev) { DR_CUDA(m, cudaEventRecord(ev[3], m->stream)); m->prof_n += 1; }
+    return rc;
+}
+
+int dr_interleave_dev(dr_model* m, const float* gathered, int32_t B, int32_t T, float* out) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!gathered || !out || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "bad argument");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    return dr_launch_interleave(m, gathered, B, T, out);
+}
+
+int dr_forward_dev(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (m->cfg.world != 1)
+        return dr_fail(m, DR_ESTATE, "dr_forward needs world == 1; sharded handles use dr_forward_local_dev / dr_forward_heads_dev");
+    int rc = check_shape(m, B, T);
+    if (rc != DR_OK) return rc;
+    rc = dr_reserve(m, (void**)&m->d_S, &m->S_cap, (size_t)B * T * DR_2H * sizeof(float));
+    if (rc != DR_OK) return rc;
+    rc = dr_forward_local_dev(m, x, B, T, m->d_S, out);     // world == 1: out_local IS out [B,T,M,Q]
+    if (rc != DR_OK) return rc;
+    return dr_forward_heads_dev(m, m->d_S, B, T, out);
+}
+
+int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!x || !out) return dr_fail(m, DR_EINVAL, "null host pointer");
+    int rc = check_shape(m, B, T);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    size_t nx = (size_t)B * T * m->cfg.F, no = (size_t)B * T * m->cfg.M * DR_Q;
+    rc = dr_reserve(m, (void**)&m->d_xin, &m->xin_cap, nx * sizeof(float));
+    if (rc != DR_OK) return rc;
+    rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float));
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(m->d_xin, x, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    rc = dr_forward_dev(m, m->d_xin, B, T, m->d_out);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(out, m->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+int dr_quantile_loss_dev(dr_model* m, const float* out, const float* y, int32_t B, int32_t T, float* loss) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!out || !y || !loss || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "bad argument");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    return dr_launch_loss(m, out, y, B, T, loss);
+}
+
+int dr_quantile_loss(dr_model* m, const float* out, const float* y, int32_t B, int32_t T, float* loss) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!out || !y || !loss || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "bad argument");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    size_t no = (size_t)B * T * m->cfg.M * DR_Q, ny = (size_t)B * T * m->cfg.M;
+    int rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float));
+    if (rc != DR_OK) return rc;
+    rc = dr_reserve(m, (void**)&m->d_y, &m->y_cap, ny * sizeof(float));
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(m->d_out, out, no * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    DR_CUDA(m, cudaMemcpyAsync(m->d_y, y, ny * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    rc = dr_launch_loss(m, m->d_out, m->d_y, B, T, m->d_loss + 4);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(loss, m->d_loss + 4, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+int dr_debug_read(dr_model* m, const char* what, float* host, size_t n) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!what || !host) return dr_fail(m, DR_EINVAL, "null argument");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    const float* src = nullptr; size_t avail = 0;
+    if (!strcmp(what, "mask")) { src = m->d_mask; avail = (size_t)m->M_loc * m->cfg.F; }
+    else if (!strcmp(what, "S")) { src = m->d_S; avail = m->S_cap / sizeof(float); }
+    else if (!strcmp(what, "ct")) { src = m->d_ct; avail = (size_t)m->M_loc * 2 * DR_Q * DR_H; }
+    else if (!strcmp(what, "bias4")) { src = m->d_bias4; avail = (size_t)m->M_loc * 2 * 4 * DR_H; }
+    else return dr_fail(m, DR_EINVAL, std::string("dr_debug_read: unknown tensor ") + what);
+    if (!src || n > avail) return dr_fail(m, DR_EINVAL, "dr_debug_read: tensor not available at that size");
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    DR_CUDA(m, cudaMemcpy(host, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return DR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,129 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/deeprest_b200.h"
+
+#define DR_GATES 3                 // (r, z, n) — torch.nn.GRU order, qrnn.py:24
+#define DR_2H (2 * DR_H)
+#define DR_PROF_MAX 256
+#define DR_KC 16                   // K-chunk of the FFMA weight stream; Fp is a multiple of it
+
+// ---- per-expert offsets inside the reference-order blob (mirror of layout.py) ----
+struct DrBlobOffsets {
+    int mask_w1, mask_b1, mask_w2, mask_b2;
+    int w_ih[2], w_hh[2], b_ih[2], b_hh[2];   // [0]=forward, [1]=reverse direction
+    int head_w, head_b;
+    int per_expert;
+};
+
+__host__ __device__ inline DrBlobOffsets dr_blob_offsets(int F) {
+    DrBlobOffsets o;
+    int off = 0;
+    o.mask_w1 = off; off += DR_H;
+    o.mask_b1 = off; off += DR_H;
+    o.mask_w2 = off; off += F * DR_H;
+    o.mask_b2 = off; off += F;
+    for (int d = 0; d < 2; ++d) {
+        o.w_ih[d] = off; off += 3 * DR_H * F;
+        o.w_hh[d] = off; off += 3 * DR_H * DR_H;
+        o.b_ih[d] = off; off += 3 * DR_H;
+        o.b_hh[d] = off; off += 3 * DR_H;
+    }
+    o.head_w = off; off += DR_Q * 4 * DR_H;
+    o.head_b = off; off += DR_Q;
+    o.per_expert = off;
+    return o;
+}
+
+struct dr_model {
+    dr_config cfg;
+    int e_lo, e_hi, M_loc;
+    int Fp;                         // F padded up to a multiple of DR_KC (zero weights/inputs)
+    DrBlobOffsets off;
+    bool loaded;
+
+    // device state
+    float* d_blob;                  // local shard, reference order          [M_loc * per_expert]
+    float* d_mask;                  // softmax feature mask, qrnn.py:34       [M_loc, F]
+    float* d_wf;                    // FFMA weight stream                     [M_loc,2,2,KT,3,64]
+    float* d_bias4;                 // (b_ir+b_hr, b_iz+b_hz, b_in, b_hn)     [M_loc,2,4,H]
+    float* d_ct;                    // own-expert head coeff C - A/(M-1)      [M_loc,2,Q,H]
+    float* d_abar;                  // mean-term head coeff A/(M-1)           [M_loc*Q, 2H]
+    float* d_hb;                    // head bias                              [M_loc*Q]
+    __nv_bfloat16* d_wtc;           // tcgen05 weight image (hi/lo bf16)      see dr_gru_tc.cu
+    size_t wtc_bytes;
+
+    // workspace, grown on demand
+    float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
+    void*  d_xtc;  size_t xtc_cap;  // x split to bf16 hi/lo [T, Bp, Fp]      (tcgen05 engine)
+    float* d_S;    size_t S_cap;    // [B,T,2H]
+    float* d_out;  size_t out_cap;  // staging for host entry points
+    float* d_xin;  size_t xin_cap;  // staging for host entry points
+    float* d_loss;                  // 1 float + partials
+    float* d_y;    size_t y_cap;
+
+    cudaStream_t stream;
+    cudaStream_t own_stream;
+    int64_t launches;
+    bool profile;
+    int prof_n;                     // forwards recorded since dr_profile(m,1)
+    cudaEvent_t* ev;                // [DR_PROF_MAX][4]: gru start/stop, head start/stop
+    int sm_count;
+    const char* last_engine;
+    std::string err;
+};
+
+int dr_fail(dr_model* m, int code, const std::string& msg);
+int dr_cuda_fail(dr_model* m, cudaError_t e, const char* what);
+
+#define DR_CUDA(m, call)                                                        \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return dr_cuda_fail((m), _e, #call);             \
+    } while (0)
+
+// profile events of the forward being recorded (nullptr when profiling is off or the ring is full)
+inline cudaEvent_t* dr_prof_slot(dr_model* m) {
+    return (m->profile && m->ev && m->prof_n < DR_PROF_MAX) ? m->ev + 4 * m->prof_n : nullptr;
+}
+
+// grows *ptr to at least `bytes` (device). Contents are NOT preserved.
+int dr_reserve(dr_model* m, void** ptr, size_t* cap, size_t bytes);
+
+// ---- kernels (host launchers) ----
+// dr_prep.cu
+int dr_launch_prep(dr_model* m);
+// dr_gru_ffma.cu
+int dr_ffma_rows_per_thread(int B);
+int dr_launch_xT(dr_model* m, const float* x_dev, int B, int T, int Bp);
+int dr_launch_gru_ffma(dr_model* m, int B, int T, int Bp, float* S_dev, float* out_local_dev);
+// dr_gru_tc.cu
+bool dr_tc_built();
+bool dr_tc_supported(const dr_model* m, int B, int T);
+int dr_tc_prep_weights(dr_model* m);
+int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev, float* out_local_dev);
+// dr_head.cu
+int dr_launch_heads(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
+int dr_launch_interleave(dr_model* m, const float* gathered, int B, int T, float* out);
+int dr_launch_loss(dr_model* m, const float* out_dev, const float* y_dev, int B, int T, float* loss_dev);
+
+// ---- small device helpers ----
+__device__ __forceinline__ float dr_sigmoid(float v) {
+    // 1/(1+exp(-v)); ex2.approx + rcp.approx keep the abs error ~1e-7 (well under the 1e-6 atol)
+    return __fdividef(1.0f, 1.0f + __expf(-v));
+}
+__device__ __forceinline__ float dr_tanh(float v) {
+    // tanh(v) = 1 - 2/(1+exp(2v)); saturates cleanly to +-1 for |v| large
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v));
+}
+__device__ __forceinline__ void dr_red_add_v4(float* addr, float a, float b, float c, float d) {
+    // vectorised fire-and-forget fp32 reduction (sm_90+): one L2 atomic transaction per 16 B
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void dr_red_add(float* addr, float a) {
+    asm volatile("red.global.add.f32 [%0], %1;" :: "l"(addr), "f"(a) : "memory");
+}

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference estimator interface, backed by libdeeprest_b200.so.
+
+``QuantileRNN`` keeps the reference's constructor, method names, argument meaning and
+error behaviour (resource-estimation/qrnn.py:6-75) so that ``estimate.py``-style code and
+the reference's own call sites (estimate.py:60,70,71,91,92) work unchanged:
+
+    model = QuantileRNN(input_size=F, num_metrics=M)      # qrnn.py:7
+    model.load_state_dict(sd); model.eval()
+    out = model(x)                                        # [B,T,F] -> [B,T,M,Q]   qrnn.py:28
+    loss = model.quantile_loss(out, y)                    # qrnn.py:58
+
+All arithmetic runs in the CUDA library through its C ABI (ctypes).  numpy arrays use the
+host entry points (copies inside the call); CUDA torch tensors use the ``*_dev`` entry
+points on torch's current stream.  There is no CPU path.
+
+Expert-sharded multi-GPU execution: pass ``process_group`` (any
+``torch.distributed`` group — NCCL on GPUs); the forward then runs
+local bi-GRUs -> all_reduce(S) -> heads -> all_gather(forecasts) -> interleave.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, layout
+
+
+def sliding_window(ts, window_size):
+    """utils.py:4-5 — stride-1 windows; like the reference it drops the final window."""
+    ts = np.asarray(ts)
+    n = len(ts) - window_size
+    if n <= 0:
+        return np.asarray([])
+    idx = np.arange(window_size)[None, :] + np.arange(n)[:, None]
+    return ts[idx]
+
+
+def _is_torch(t):
+    return type(t).__module__.startswith("torch")
+
+
+class QuantileRNN:
+    def __init__(self, input_size, num_metrics, hidden_layer_size=128, num_layers=1, bidirectional=True,
+                 quantiles=(.05, .50, .95), dropout=0.50, *, engine="auto", device=None,
+                 process_group=None, rank=None, world=None):
+        if hidden_layer_size != layout.H or num_layers != 1 or not bidirectional:
+            raise NotImplementedError(
+                "libdeeprest_b200 implements the reference defaults only: hidden_layer_size=128, "
+                "num_layers=1, bidirectional=True (qrnn.py:7)")
+        if len(quantiles) != layout.Q:
+            raise NotImplementedError("exactly 3 quantiles are supported (reference default, qrnn.py:8)")
+        self.input_size, self.num_metrics = int(input_size), int(num_metrics)
+        self.hidden_layer_size, self.num_layers, self.bidirectional = hidden_layer_size, num_layers, bidirectional
+        self.quantiles, self.dropout_p = tuple(float(q) for q in quantiles), float(dropout)
+        self.training = True                     # nn.Module default
+        self._pg = process_group
+        if process_group is not None or (world or 1) > 1:
+            import torch.distributed as dist
+            rank = dist.get_rank(process_group) if rank is None else rank
+            world = dist.get_world_size(process_group) if world is None else world
+        self.rank, self.world = int(rank or 0), int(world or 1)
+        if device is None:
+            device = 0
+            try:
+                import torch
+                if torch.cuda.is_available():
+                    device = torch.cuda.current_device()
+            except ImportError:
+                pass
+        self.device = int(device)
+        self._lib = _lib.load()
+        cfg = _lib.DrConfig(F=self.input_size, M=self.num_metrics, H=layout.H, Q=layout.Q,
+                            dropout_p=self.dropout_p, engine=_lib.ENGINES[engine], device=self.device,
+                            rank=self.rank, world=self.world)
+        for i, q in enumerate(self.quantiles):
+            cfg.quantiles[i] = q
+        self._h = C.c_void_p()
+        rc = self._lib.dr_create(C.byref(cfg), C.byref(self._h))
+        if rc != _lib.DR_OK:
+            msg = self._lib.dr_last_error(None).decode()
+            if self.num_metrics < 2:
+                # the reference fails here too: torch.stack([]) raises RuntimeError (qrnn.py:52)
+                raise RuntimeError(msg)
+            raise _lib.DeepRestError(rc, msg)
+        self.m_local = self.num_metrics // self.world
+
+    # ---- lifecycle -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.dr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to(self, device):                         # estimate.py:60 — handle is already on its GPU
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    # ---- weights ---------------------------------------------------------------------
+    def load_blob(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.float32).reshape(-1)
+        _lib.check(self._h, self._lib.dr_load_weights(
+            self._h, blob.ctypes.data_as(C.POINTER(C.c_float)), blob.size))
+        return self
+
+    def load_state_dict(self, sd):
+        return self.load_blob(layout.blob_from_state_dict(sd, self.num_metrics, self.input_size))
+
+    def blob(self):
+        out = np.zeros(layout.blob_size(self.num_metrics, self.input_size), np.float32)
+        _lib.check(self._h, self._lib.dr_get_weights(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), out.size))
+        return out
+
+    def state_dict(self):
+        return layout.state_dict_from_blob(self.blob(), self.num_metrics, self.input_size)
+
+    # ---- forward ---------------------------------------------------------------------
+    def __call__(self, input_seq, out=None):
+        return self.forward(input_seq, out=out)
+
+    def forward(self, input_seq, out=None):
+        if self.training and self.dropout_p > 0:
+            raise NotImplementedError(
+                "training-mode forward (dropout + autograd, qrnn.py:43 / estimate.py:70-74) is served by "
+                "train_step(); call .eval() for inference")
+        if _is_torch(input_seq) and input_seq.is_cuda:
+            return self._forward_torch(input_seq)
+        if self.world != 1:
+            raise ValueError("sharded handles take CUDA torch tensors (the collectives run on device buffers)")
+        x = np.ascontiguousarray(input_seq.detach().cpu().numpy() if _is_torch(input_seq) else input_seq,
+                                 dtype=np.float32)
+        if x.ndim != 3 or x.shape[2] != self.input_size:
+            raise ValueError(f"input_seq must be [B,T,{self.input_size}], got {x.shape}")
+        B, T, _ = x.shape
+        if out is None:
+            out = np.empty((B, T, self.num_metrics, layout.Q), np.float32)
+        elif out.shape != (B, T, self.num_metrics, layout.Q) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 [B,T,M,Q] array (pinned memory makes the D2H copy fast)")
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_forward(self._h, x.ctypes.data_as(fp), B, T, out.ctypes.data_as(fp)))
+        if _is_torch(input_seq):
+            import torch
+            return torch.from_numpy(out)
+        return out
+
+    def _bind_stream(self):
+        import torch
+        _lib.check(self._h, self._lib.dr_set_stream(
+            self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+
+    def _forward_torch(self, x):
+        import torch
+        if x.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.input_size:
+            raise ValueError(f"input_seq must be float32 [B,T,{self.input_size}]")
+        x = x.contiguous()
+        B, T, _ = x.shape
+        self._bind_stream()
+        if self.world == 1:
+            out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
+            _lib.check(self._h, self._lib.dr_forward_dev(self._h, x.data_ptr(), B, T, out.data_ptr()))
+            return out
+        import torch.distributed as dist
+        S = torch.empty((B, T, 2 * layout.H), device=x.device, dtype=torch.float32)
+        out_local = torch.empty((B, T, self.m_local, layout.Q), device=x.device, dtype=torch.float32)
+        _lib.check(self._h, self._lib.dr_forward_local_dev(self._h, x.data_ptr(), B, T, S.data_ptr(), out_local.data_ptr()))
+        dist.all_reduce(S, op=dist.ReduceOp.SUM, group=self._pg)          # the one exchange step
+        _lib.check(self._h, self._lib.dr_forward_heads_dev(self._h, S.data_ptr(), B, T, out_local.data_ptr()))
+        gathered = torch.empty((self.world, B, T, self.m_local, layout.Q), device=x.device, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, out_local, group=self._pg)
+        out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
+        _lib.check(self._h, self._lib.dr_interleave_dev(self._h, gathered.data_ptr(), B, T, out.data_ptr()))
+        return out
+
+    # ---- loss ------------------------------------------------------------------------
+    def quantile_loss(self, outputs, labels):
+        if _is_torch(outputs) and outputs.is_cuda:
+            import torch
+            self._bind_stream()
+            B, T = outputs.shape[:2]
+            loss = torch.empty((), device=outputs.device, dtype=torch.float32)
+            _lib.check(self._h, self._lib.dr_quantile_loss_dev(
+                self._h, outputs.contiguous().data_ptr(), labels.contiguous().data_ptr(), B, T, loss.data_ptr()))
+            return loss
+        o = np.ascontiguousarray(outputs.detach().cpu().numpy() if _is_torch(outputs) else outputs, np.float32)
+        y = np.ascontiguousarray(labels.detach().cpu().numpy() if _is_torch(labels) else labels, np.float32)
+        if o.ndim != 4 or y.shape != o.shape[:3]:
+            raise ValueError("outputs must be [B,T,M,Q] and labels [B,T,M]")
+        loss = C.c_float()
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_quantile_loss(self._h, o.ctypes.data_as(fp), y.ctypes.data_as(fp),
+                                                       o.shape[0], o.shape[1], C.byref(loss)))
+        return np.float32(loss.value)
+
+    # ---- helpers either side of the path -----------------------------------------------
+    @staticmethod
+    def normalization_minmax(M, split):
+        """qrnn.py:69-75 — host-side min-max over the train split (identity if constant)."""
+        head = np.asarray(M)[:split]
+        lo, hi = head.min(), head.max()
+        span = hi - lo
+        return ((M - lo) / span if span != 0.0 else M), lo, hi
+
+    # ---- diagnostics -------------------------------------------------------------------
+    def debug_read(self, what, n):
+        buf = np.empty(n, np.float32)
+        _lib.check(self._h, self._lib.dr_debug_read(self._h, what.encode(), buf.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return buf
+
+    def profile(self, enable=True):
+        _lib.check(self._h, self._lib.dr_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(forwards recorded, sum of recurrence-kernel ms, sum of head-kernel ms) since profile(True)."""
+        n, g, h = C.c_int32(), C.c_float(), C.c_float()
+        _lib.check(self._h, self._lib.dr_profile_read(self._h, C.byref(n), C.byref(g), C.byref(h)))
+        return n.value, g.value, h.value
+
+    @property
+    def launch_count(self):
+        return int(self._lib.dr_launch_count(self._h))
+
+    @property
+    def last_engine(self):
+        return self._lib.dr_last_engine(self._h).decode()

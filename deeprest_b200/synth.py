@@ -57,19 +57,23 @@ def labels(seed: int, B: int, T: int, M: int) -> np.ndarray:
     return uniform(seed, B * T * M).reshape(B, T, M)
 
 
-def weights(seed: int, M: int, F: int, scale: float = 1.0) -> np.ndarray:
+def weights(seed: int, M: int, F: int, scale: float = 1.0, experts=None) -> np.ndarray:
     """A full weight blob with the reference's default-init *distribution*.
 
     torch defaults: ``nn.Linear`` U(±1/sqrt(fan_in)), ``nn.GRU``
     U(±1/sqrt(H)).  ``scale`` > 1 widens every range to mimic trained weights
     with saturating gates.  Values come from :func:`uniform`, so the blob is a
-    pure function of (seed, M, F, scale).
+    pure function of (seed, M, F, scale).  ``experts=(lo, hi)`` fills only that shard of the
+    full-size blob (the rest stays zero) — what a sharded rank needs, without generating all M.
     """
     from .layout import H, expert_offsets, params_per_expert
 
     pe = params_per_expert(F)
-    u = uniform(seed, M * pe).reshape(M, pe)
-    blob = np.empty((M, pe), np.float32)
+    lo, hi = (0, M) if experts is None else experts
+    blob = np.zeros((M, pe), np.float32)
+    if hi <= lo:
+        return blob.reshape(-1)
+    u = uniform(seed, (hi - lo) * pe, offset=lo * pe).reshape(hi - lo, pe)
     bound = {
         "mask_w1": 1.0, "mask_b1": 1.0,                    # fan_in = 1
         "mask_w2": 1.0 / np.sqrt(H), "mask_b2": 1.0 / np.sqrt(H),
@@ -78,5 +82,5 @@ def weights(seed: int, M: int, F: int, scale: float = 1.0) -> np.ndarray:
     for name, (off, shape) in expert_offsets(F).items():
         n = int(np.prod(shape))
         b = np.float32(bound.get(name, 1.0 / np.sqrt(H)) * scale)
-        blob[:, off:off + n] = (u[:, off:off + n] * np.float32(2.0) - np.float32(1.0)) * b
+        blob[lo:hi, off:off + n] = (u[:, off:off + n] * np.float32(2.0) - np.float32(1.0)) * b
     return blob.reshape(-1)

@@ -1,0 +1,131 @@
+/*
+ * deeprest_b200.h — C ABI of libdeeprest_b200.so, the B200-native replacement for the
+ * DeepRest resource-estimator hot path (reference: resource-estimation/qrnn.py:6-67,
+ * driven from resource-estimation/estimate.py:60-107).
+ *
+ * The reference has no FFI: the path is a torch nn.Module called in-process
+ * (SURVEY §8b).  Each entry point below names the reference interface it replaces.
+ * The ABI is cgo/ctypes/JNI-safe by construction: C types only, no callbacks, no
+ * exceptions across the boundary, no caller pointer retained after a call returns.
+ *
+ * Conventions
+ *   - every function returns 0 (DR_OK) or a negative DR_E* code; the message for the last
+ *     failure on a handle is dr_last_error(handle) (dr_last_error(NULL) for dr_create).
+ *   - host entry points (no _dev suffix) take HOST pointers, copy in/out, and return only
+ *     when the result is in the caller's buffer.
+ *   - *_dev entry points take DEVICE pointers and are asynchronous on the handle's stream.
+ *   - a handle is not thread-safe; distinct handles are independent. One handle per GPU.
+ *   - there is NO CPU fallback: without a CUDA device dr_create fails with DR_ECUDA.
+ *
+ * Shapes (reference notation): B windows, T seq_len, F input features, M experts
+ * (= component_resource series, qrnn.py:21), H = 128, Q = 3 quantiles.
+ * Weight blob = the reference state_dict() order without mask_init (see
+ * deeprest_b200/layout.py).
+ */
+#ifndef DEEPREST_B200_H
+#define DEEPREST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DR_OK            0
+#define DR_EINVAL       -1   /* bad argument / shape                                        */
+#define DR_ECUDA        -2   /* CUDA runtime failure or no device                           */
+#define DR_ENOMEM       -3   /* device or host allocation failed                            */
+#define DR_ESTATE       -4   /* call order (e.g. forward before load_weights)               */
+#define DR_EUNSUPPORTED -5   /* hyper-parameter the reference allows but this build does not */
+
+#define DR_H 128
+#define DR_Q 3
+
+/* engine selection for the bi-GRU recurrence */
+#define DR_ENGINE_AUTO  0    /* tcgen05 for large batches, FFMA for small ones              */
+#define DR_ENGINE_FFMA  1    /* fp32 CUDA-core kernel (exact fp32 accumulate)               */
+#define DR_ENGINE_TC    2    /* tcgen05 tensor-core kernel, split-bf16 (3-pass) operands    */
+
+typedef struct dr_model dr_model;
+
+/* Mirrors QuantileRNN.__init__(input_size, num_metrics, hidden_layer_size=128, num_layers=1,
+ * bidirectional=True, quantiles=(.05,.5,.95), dropout=.5)  — qrnn.py:7-8.
+ * H, num_layers and bidirectional are fixed to the reference defaults. */
+typedef struct dr_config {
+    int32_t F;              /* input_size                                                   */
+    int32_t M;              /* num_metrics (global, >= 2: the reference crashes at 1)       */
+    int32_t H;              /* must be 128                                                  */
+    int32_t Q;              /* must be 3                                                    */
+    float   quantiles[8];   /* first Q used                                                 */
+    float   dropout_p;      /* training only                                                */
+    int32_t engine;         /* DR_ENGINE_*                                                  */
+    int32_t device;         /* CUDA ordinal                                                 */
+    int32_t rank, world;    /* expert shard: this handle owns experts [rank*M/world, ...)   */
+} dr_config;
+
+/* ---- lifecycle: replaces QuantileRNN(...).to(device)  (estimate.py:60) ---- */
+int  dr_create(const dr_config* cfg, dr_model** out);
+void dr_destroy(dr_model* m);
+const char* dr_last_error(const dr_model* m);
+int  dr_version(void);
+/* 1 if this build contains the given DR_ENGINE_* recurrence engine */
+int  dr_has_engine(int32_t engine);
+
+/* optional: run on a caller-owned CUDA stream. use_caller_stream == 0 restores the handle's own
+ * (non-blocking) stream; != 0 adopts cuda_stream (a cudaStream_t; NULL = the legacy default stream) */
+int  dr_set_stream(dr_model* m, void* cuda_stream, int32_t use_caller_stream);
+/* experts owned by this handle: [*lo, *hi) */
+int  dr_local_experts(const dr_model* m, int32_t* lo, int32_t* hi);
+
+/* ---- weights: replaces load_state_dict()/state_dict() (the reference never saves) ----
+ * blob is the FULL model (M experts); the handle keeps only its shard. dr_get_weights writes
+ * the local shard into its slot of a full-size blob and leaves the rest untouched. */
+int  dr_load_weights(dr_model* m, const float* host_blob, size_t n_floats);
+int  dr_get_weights (dr_model* m, float* host_blob, size_t n_floats);
+
+/* ---- forward: replaces QuantileRNN.forward in eval mode (qrnn.py:28-56; estimate.py:91) ----
+ * x [B,T,F] fp32 -> out [B,T,M,Q] fp32.  Requires world == 1. */
+int  dr_forward    (dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host);
+int  dr_forward_dev(dr_model* m, const float* x_dev,  int32_t B, int32_t T, float* out_dev);
+
+/* ---- expert-sharded forward, device pointers, async ----
+ *   1. dr_forward_local_dev : local bi-GRUs.  Writes S_dev[B,T,2H] = sum over LOCAL experts of
+ *      their GRU outputs, and out_local_dev[B,T,M_loc,Q] = own-expert part of the heads.
+ *   2. caller all-reduces (sum) S_dev across ranks (torch.distributed / NCCL).
+ *   3. dr_forward_heads_dev : adds the cross-expert-mean term and bias into out_local_dev.
+ *   4. caller all-gathers out_local into gathered[world][B,T,M_loc,Q];
+ *      dr_interleave_dev reorders it to the reference layout out[B,T,M,Q] (qrnn.py:55). */
+int  dr_forward_local_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T,
+                          float* S_dev, float* out_local_dev);
+int  dr_forward_heads_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
+                          float* out_local_dev);
+int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int32_t T,
+                          float* out_dev);
+
+/* ---- loss: replaces QuantileRNN.quantile_loss (qrnn.py:58-67) ----
+ * out [B,T,M,Q], y [B,T,M] -> scalar pinball loss (mean over M of mean over B,T of sum over Q) */
+int  dr_quantile_loss    (dr_model* m, const float* out_host, const float* y_host,
+                          int32_t B, int32_t T, float* loss_host);
+int  dr_quantile_loss_dev(dr_model* m, const float* out_dev, const float* y_dev,
+                          int32_t B, int32_t T, float* loss_dev);
+
+/* ---- test/diagnostic access to prepared tensors (not on the hot path) ----
+ * what: "mask" [M_loc,F] (qrnn.py:34), "S" [B,T,2H] of the last forward, "launches" (1 int64
+ * as float pair is NOT used; see dr_launch_count). Returns DR_EINVAL for unknown names. */
+int  dr_debug_read(dr_model* m, const char* what, float* host_buf, size_t n_floats);
+/* per-kernel device timing (CUDA events on the launching stream). dr_profile(m,1) clears the
+ * record and makes every forward (up to 256) record events around the recurrence kernel and the
+ * head kernel; dr_profile_read synchronises and returns how many forwards were recorded and the
+ * SUM of their kernel durations in milliseconds. */
+int  dr_profile(dr_model* m, int32_t enable);
+int  dr_profile_read(dr_model* m, int32_t* n_forwards, float* gru_ms_sum, float* head_ms_sum);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t dr_launch_count(const dr_model* m);
+/* name of the GRU engine the last forward used: "ffma" or "tcgen05" */
+const char* dr_last_engine(const dr_model* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPREST_B200_H */

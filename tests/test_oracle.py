@@ -79,3 +79,10 @@ def test_pinball_grad_matches_finite_differences():
         m = out.copy(); m[idx] -= eps
         fd = (oracle.quantile_loss(p, y, dtype=np.float64) - oracle.quantile_loss(m, y, dtype=np.float64)) / (2 * eps)
         assert abs(fd - g[idx]) < 1e-6
+
+
+def test_torch_cpu_baseline_port_matches_reference_golden():
+    from oracle.qrnn_torch_cpu import TorchCpuPort
+    g = load_golden(os.path.join(GOLDEN_DIR, "g2b_small_diurnal.npz"))
+    out = TorchCpuPort(g["blob_arr"], g["M"], g["F"]).forward(g["x"])
+    assert np.abs(out - g["out"]).max() < 1e-7     # same torch kernels as the reference
