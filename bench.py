@@ -103,6 +103,28 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- helpers
+T0 = time.perf_counter()
+
+
+def log(msg):
+    print(f"[bench +{time.perf_counter() - T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def host_cores():
+    """Cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 def algorithmic_flops(M_loc, B, T, F):
     """forward FLOPs per expert-window-step = 1536*F + 199,680."""
     return float(1536 * F + 199680) * M_loc * B * T
@@ -138,16 +160,21 @@ def cpu_sample(blob, M, F, x, budget_s):
     """Time the reference-algorithm CPU port on a bounded sample: all M experts, the first n windows."""
     import torch
     from oracle.qrnn_torch_cpu import TorchCpuPort
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     port = TorchCpuPort(blob, M, F)
+    log(f"cpu baseline: calibrating on 1 window x {M} experts with {cores} threads")
     t0 = time.perf_counter()
-    port.forward(x[:1])
+    ref = port.forward(x[:1])
     t1 = time.perf_counter() - t0
     n = int(max(1, min(16, budget_s / max(t1, 1e-3), x.shape[0])))
-    t0 = time.perf_counter()
-    ref = port.forward(x[:n])
-    dt = time.perf_counter() - t0
+    dt = t1
+    if n > 1:
+        log(f"cpu baseline: 1 window took {t1:.2f}s -> timing {n} windows")
+        t0 = time.perf_counter()
+        ref = port.forward(x[:n])
+        dt = time.perf_counter() - t0
+    log(f"cpu baseline: {n} windows in {dt:.2f}s")
     return {"n": n, "seconds": dt, "out": ref, "cores": cores, "torch": torch.__version__}
 
 
@@ -163,10 +190,12 @@ def run_reference(args, rank):
     x = synth.windows(XSEED, min(B, 16), T, F)
     import torch
     from oracle.qrnn_torch_cpu import TorchCpuPort
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     port = TorchCpuPort(blob, M, F)
+    log(f"reference arm: {cores} threads, calibrating")
     t0 = time.perf_counter(); port.forward(x[:1]); t1 = time.perf_counter() - t0
+    log(f"reference arm: 1 window x {M} experts = {t1:.2f}s")
     total_steps = args.steps + args.warmup
     n = int(max(1, min(x.shape[0], (150.0 / total_steps) / max(t1, 1e-3))))
     for _ in range(args.warmup):
@@ -216,6 +245,7 @@ def run_ours(args, rank, world, local_rank):
                         process_group=pg, rank=rank, world=world).eval()
     model.load_blob(blob)
     x_dev = x_host.to(dev)
+    log(f"model ready: M={M} (local {M_loc}) B={B} T={T} F={F}")
 
     def barrier():
         if world > 1:
@@ -232,9 +262,13 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     # ---- device-resident throughput (`value`) ----
-    for _ in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 3)):
         out = model(x_dev)
+        if i == 0:
+            torch.cuda.synchronize()
+            log(f"first forward done (engine {model.last_engine})")
     barrier()
+    log("warm-up done")
     model.profile(True)
     launches0 = model.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -251,6 +285,8 @@ def run_ours(args, rank, world, local_rank):
     model.profile(False)
     ms_step = ms_total / args.steps
     value = S * B / (ms_step * 1e-3)
+    log(f"device-resident: {ms_step:.2f} ms/step, recurrence kernel {gru_ms_sum / max(n_prof, 1):.2f} ms, "
+        f"head kernel {head_ms_sum / max(n_prof, 1):.2f} ms")
 
     # ---- end to end through the public API with host buffers (`e2e`) ----
     h2d = x_host.numel() * 4
@@ -277,6 +313,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     e2e_value = S * B / e2e_s
+    log(f"e2e: {e2e_s * 1e3:.2f} ms/step")
 
     # ---- roofline of the dominant kernel (the bi-GRU recurrence) ----
     peaks = measured_peaks()

@@ -42,12 +42,15 @@ SIGNATURES = {
     "dr_get_weights": (C.c_int, [_H, _FP, C.c_size_t]),
     "dr_forward": (C.c_int, [_H, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_forward_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dr_s_elems": (C.c_int64, [C.c_int32, C.c_int32]),
     "dr_forward_local_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dr_forward_heads_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_interleave_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_quantile_loss": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_quantile_loss_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_debug_read": (C.c_int, [_H, C.c_char_p, _FP, C.c_size_t]),
+    "dr_tc_probe": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                              C.c_int32, C.c_int32, C.c_int32, _FP]),
     "dr_launch_count": (C.c_int64, [_H]),
     "dr_last_engine": (C.c_char_p, [_H]),
 }

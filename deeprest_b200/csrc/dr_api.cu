@@ -159,6 +159,8 @@ int dr_local_experts(const dr_model* m, int32_t* lo, int32_t* hi) {
     return DR_OK;
 }
 
+int64_t dr_s_elems(int32_t B, int32_t T) { return (B < 1 || T < 1) ? -1 : (int64_t)dr_s_floats(B, T); }
+
 int64_t dr_launch_count(const dr_model* m) { return m ? m->launches : -1; }
 const char* dr_last_engine(const dr_model* m) { return m ? m->last_engine : "none"; }
 
@@ -193,6 +195,7 @@ int dr_get_weights(dr_model* m, float* blob, size_t n) {
 
 static int check_shape(dr_model* m, int B, int T) {
     if (B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "B and T must be >= 1");
+    if (T > 65535) return dr_fail(m, DR_EINVAL, "T too large (max 65535)");
     if ((long long)B * T > (1LL << 31) / DR_2H) return dr_fail(m, DR_EINVAL, "B*T too large for one call; split the batch");
     if (!m->loaded) return dr_fail(m, DR_ESTATE, "forward before dr_load_weights");
     return DR_OK;
@@ -205,7 +208,7 @@ int dr_forward_local_dev(dr_model* m, const float* x, int32_t B, int32_t T, floa
     if (!x || !S || !out_local) return dr_fail(m, DR_EINVAL, "null device pointer");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     size_t R = (size_t)B * T;
-    DR_CUDA(m, cudaMemsetAsync(S, 0, R * DR_2H * sizeof(float), m->stream));
+    DR_CUDA(m, cudaMemsetAsync(S, 0, dr_s_floats(B, T) * sizeof(float), m->stream));
     DR_CUDA(m, cudaMemsetAsync(out_local, 0, R * m->M_loc * DR_Q * sizeof(float), m->stream));
     if (m->M_loc == 0) return DR_OK;
 
@@ -255,7 +258,7 @@ int dr_forward_dev(dr_model* m, const float* x, int32_t B, int32_t T, float* out
         return dr_fail(m, DR_ESTATE, "dr_forward needs world == 1; sharded handles use dr_forward_local_dev / dr_forward_heads_dev");
     int rc = check_shape(m, B, T);
     if (rc != DR_OK) return rc;
-    rc = dr_reserve(m, (void**)&m->d_S, &m->S_cap, (size_t)B * T * DR_2H * sizeof(float));
+    rc = dr_reserve(m, (void**)&m->d_S, &m->S_cap, dr_s_floats(B, T) * sizeof(float));
     if (rc != DR_OK) return rc;
     rc = dr_forward_local_dev(m, x, B, T, m->d_S, out);     // world == 1: out_local IS out [B,T,M,Q]
     if (rc != DR_OK) return rc;

@@ -59,7 +59,7 @@ struct dr_model {
     // workspace, grown on demand
     float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
     void*  d_xtc;  size_t xtc_cap;  // x split to bf16 hi/lo [T, Bp, Fp]      (tcgen05 engine)
-    float* d_S;    size_t S_cap;    // [B,T,2H]
+    float* d_S;    size_t S_cap;    // [T][2H/4][Bp][4]
     float* d_out;  size_t out_cap;  // staging for host entry points
     float* d_xin;  size_t xin_cap;  // staging for host entry points
     float* d_loss;                  // 1 float + partials
@@ -89,6 +89,10 @@ int dr_cuda_fail(dr_model* m, cudaError_t e, const char* what);
 inline cudaEvent_t* dr_prof_slot(dr_model* m) {
     return (m->profile && m->ev && m->prof_n < DR_PROF_MAX) ? m->ev + 4 * m->prof_n : nullptr;
 }
+
+// S (cross-expert sum) is stored k-group major: [T][2H/4][dr_s_rows(B)][4] floats
+inline int dr_s_rows(int B) { return (B + 127) / 128 * 128; }
+inline size_t dr_s_floats(int B, int T) { return (size_t)T * DR_2H * dr_s_rows(B); }
 
 // grows *ptr to at least `bytes` (device). Contents are NOT preserved.
 int dr_reserve(dr_model* m, void** ptr, size_t* cap, size_t bytes);

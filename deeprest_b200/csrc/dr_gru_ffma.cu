@@ -53,9 +53,9 @@ dr_gru_ffma_kernel(const float* __restrict__ xT,     // [T][Fp][Bp]
                    const float* __restrict__ wf,     // [M_loc][2][2][KT][3][64]
                    const float* __restrict__ bias4,  // [M_loc][2][4][H]
                    const float* __restrict__ ct,     // [M_loc][2][Q][H]
-                   float* __restrict__ S,            // [B][T][2H]
+                   float* __restrict__ S,            // [T][2H/4][BpS][4]  (k-group major: coalesced REDs)
                    float* __restrict__ out_local,    // [B][T][M_loc][Q]
-                   int B, int T, int Fp, int Bp, int M_loc) {
+                   int B, int T, int Fp, int Bp, int BpS, int M_loc) {
     constexpr int BT = Cfg<RPT>::BT;
     constexpr int NS = Cfg<RPT>::NSTAGE;
     extern __shared__ __align__(16) float smem[];
@@ -196,7 +196,7 @@ dr_gru_ffma_kernel(const float* __restrict__ xT,     // [T][Fp][Bp]
             for (int i = 0; i < RPT; ++i) {
                 int b = b0 + r0 + i;
                 if (b < B)
-                    dr_red_add_v4(S + ((size_t)b * T + tt) * DR_2H + dir * DR_H + p * 64 + tx * 4,
+                    dr_red_add_v4(S + (((size_t)tt * 64 + dir * 32 + p * 16 + tx) * BpS + b) * 4,
                                   hn[i][0], hn[i][1], hn[i][2], hn[i][3]);
             }
         }
@@ -245,6 +245,7 @@ __global__ void dr_xT_kernel(const float* __restrict__ x, float* __restrict__ xT
 
 template <int RPT>
 int launch_one(dr_model* m, int B, int T, int Bp, float* S, float* out_local) {
+    const int BpS = dr_s_rows(B);
     constexpr int BT = Cfg<RPT>::BT;
     int Fp = m->Fp;
     size_t smem = ((size_t)Fp * BT + 2 * DR_H * BT + Cfg<RPT>::NSTAGE * kChunkFloats + 4 * DR_H + DR_Q * DR_H) * sizeof(float);
@@ -252,7 +253,7 @@ int launch_one(dr_model* m, int B, int T, int Bp, float* S, float* out_local) {
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_ffma_kernel<RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(Bp / BT, 2, m->M_loc);
     dr_gru_ffma_kernel<RPT><<<grid, kThreads, smem, m->stream>>>(m->d_xT, m->d_wf, m->d_bias4, m->d_ct, S, out_local,
-                                                                 B, T, Fp, Bp, m->M_loc);
+                                                                 B, T, Fp, Bp, BpS, m->M_loc);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;

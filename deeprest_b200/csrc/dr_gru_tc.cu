@@ -1,8 +1,392 @@
-// K1 (tensor-core engine) — placeholder until the tcgen05 kernel lands.
+// K1 (tensor-core engine) — fused bidirectional-GRU recurrence on tcgen05 / TMEM.
+//
+// Same contract as the FFMA engine (dr_gru_ffma.cu): for every local expert and both directions,
+// run the GRU over T steps (qrnn.py:33-42), add h_t into the cross-expert sum S and the
+// own-expert head term into out_local (qrnn.py:46-54 folded).
+//
+// fp32 parity on bf16 tensor cores: every operand is split v = hi + lo (two bf16, ~16 mantissa
+// bits) and each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
+// ("3-pass"); the dropped lo*lo term is ~2^-18 relative.
+//
+// One work item = (expert, direction, 256-window pair tile), run by a 2-CTA cluster with
+// cta_group::2 MMAs (M = 256: 128 windows per CTA).  Why a pair: the split weight image of one
+// expert-direction is 288 KB — it only fits on chip when each SM holds half of the B operand.
+//   shared memory / CTA : weight image 144 KB (4 hidden-quarters x {Wx hi,lo ; Wh hi,lo x 2 K-blocks}),
+//                         x tiles 2 stages x {hi,lo} x 16 KB, all pre-swizzled SW128 K-major images
+//                         moved by 1-D bulk (TMA engine) copies.
+//   TMEM / CTA (512 col): 2 gate buffers x 128 fp32 columns [gi_n | r | z | gh_n] x 32 hidden units,
+//                         2 h-operand buffers x 128 columns (bf16 hi | lo, two per column): the
+//                         recurrent A operand never touches shared memory (tcgen05.st -> MMA.TS).
+//   warps               : 0-7 gate epilogue (TMEM lane quarter = w%4, hidden half = w/4),
+//                         8 MMA issuer (leader CTA), 9 bulk-copy producer.
+// Per step and hidden-quarter q:  x-part  D[:,0:96]   = x_t  * [W_in|W_ir|W_iz]_q^T   (A from smem)
+//                                 h-part  D[:,32:128] += h    * [W_hr|W_hz|W_hn]_q^T   (A from TMEM)
+// so r and z accumulate both parts while gi_n / gh_n stay separate (n = tanh(gi_n + r*gh_n)).
 #include "dr_common.cuh"
-bool dr_tc_built() { return false; }
-bool dr_tc_supported(const dr_model*, int, int) { return false; }
-int dr_tc_prep_weights(dr_model*) { return DR_OK; }
-int dr_launch_gru_tc(dr_model* m, const float*, int, int, float*, float*) {
-    return dr_fail(m, DR_EUNSUPPORTED, "tcgen05 engine not built");
+#include "dr_tc.cuh"
+
+using namespace drtc;
+
+namespace {
+
+constexpr int kThreads = 320;
+constexpr int kEpiWarps = 8;
+constexpr int kMmaWarp = 8, kLoadWarp = 9;
+constexpr uint32_t kBlk = 48 * 128;                 // one B block: 48 rows x 64 K (bf16) = 6 KB
+constexpr uint32_t kQuarterBytes = 6 * kBlk;        // Wx_hi, Wx_lo, Wh_hi[2], Wh_lo[2]
+constexpr uint32_t kWBytes = 4 * kQuarterBytes;     // 147456 per CTA
+constexpr uint32_t kXTile = 128 * 128;              // one x part: 128 rows x 64 features (bf16) = 16 KB
+constexpr uint32_t kXStage = 2 * kXTile;            // hi + lo
+// TMEM columns
+constexpr uint32_t kG0 = 0, kHA = 256, kHB = 384;
+// shared memory map
+constexpr uint32_t kOffW = 0;
+constexpr uint32_t kOffX = kWBytes;                         // 2 stages
+constexpr uint32_t kOffBias = kOffX + 2 * kXStage;          // 4*H floats
+constexpr uint32_t kOffCt = kOffBias + 4 * DR_H * 4;        // Q*H floats
+constexpr uint32_t kOffBar = kOffCt + DR_Q * DR_H * 4;      // barriers
+constexpr uint32_t kSmemBytes = kOffBar + 256;
+
+enum Bar { GATE_FULL0 = 0, GATE_FULL1, GATE_FREE0, GATE_FREE1, H_READY, X_FULL0, X_FULL1, X_FREE0, X_FREE1,
+           X_LAND0, X_LAND1, W_LAND, W_READY, NUM_BARS };
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][kWBytes]
+                 const uint8_t* __restrict__ xtc,     // [T][ntiles][2 cta][hi|lo][kXTile]
+                 const float* __restrict__ bias4,     // [M_loc][2][4][H]
+                 const float* __restrict__ ct,        // [M_loc][2][Q][H]
+                 float* __restrict__ S,               // [T][64][Bp][4]
+                 float* __restrict__ out_local,       // [B][T][M_loc][Q]
+                 int B, int T, int Bp, int M_loc, int ntiles) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t cta = cluster_ctarank();
+    const int item = blockIdx.x >> 1;                 // (e, dir, tile)
+    const int tile = item % ntiles;
+    const int dir = (item / ntiles) & 1;
+    const int e = item / (2 * ntiles);
+
+    float* bs = reinterpret_cast<float*>(smem + kOffBias);
+    float* cs = reinterpret_cast<float*>(smem + kOffCt);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+    auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+    for (int i = tid; i < 4 * DR_H; i += kThreads) bs[i] = bias4[(size_t)(e * 2 + dir) * 4 * DR_H + i];
+    for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i];
+    if (tid == 0) {
+        mbar_init(bar(GATE_FULL0), 1); mbar_init(bar(GATE_FULL1), 1);
+        mbar_init(bar(GATE_FREE0), 2 * kEpiWarps); mbar_init(bar(GATE_FREE1), 2 * kEpiWarps);
+        mbar_init(bar(H_READY), 2 * kEpiWarps);
+        mbar_init(bar(X_FULL0), 2); mbar_init(bar(X_FULL1), 2);
+        mbar_init(bar(X_FREE0), 1); mbar_init(bar(X_FREE1), 1);
+        mbar_init(bar(X_LAND0), 1); mbar_init(bar(X_LAND1), 1);
+        mbar_init(bar(W_LAND), 1); mbar_init(bar(W_READY), 2);
+        fence_mbar_init();
+    }
+    if (warp == kMmaWarp) { tmem_alloc<2>(smem_u32(tmem_slot), 512); tmem_relinquish<2>(); }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+
+    if (warp < kEpiWarps) {
+        // ======================= gate epilogue warps =======================
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int half = warp >> 2;                               // which 16 of the quarter's 32 hidden units
+        const int row = (warp & 3) * 32 + lane;                   // TMEM lane == window row in this CTA
+        const int b = tile * 256 + (int)cta * 128 + row;
+        const bool live = b < B;
+
+        // ---- init: h0 = 0 (qrnn.py:39), gh_n accumulator columns = 0, then publish "previous step done"
+        {
+            uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int c = 0; c < 64; c += 8) tmem_st8(tbase + lane_base + kHA + half * 64 + c, z8);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                tmem_st8(tbase + lane_base + kG0 + g * 128 + 96 + half * 16, z8);
+                tmem_st8(tbase + lane_base + kG0 + g * 128 + 96 + half * 16 + 8, z8);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster(bar(H_READY), 0);
+                mbar_arrive_cluster(bar(GATE_FREE0), 0);
+                mbar_arrive_cluster(bar(GATE_FREE1), 0);
+            }
+        }
+
+        float hreg[4][16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hreg[q][j] = 0.0f;
+
+        uint32_t full_phase[2] = {0, 0};
+        for (int s = 0; s < T; ++s) {
+            const int tt = dir ? (T - 1 - s) : s;
+            const uint32_t hnext = (s & 1) ? kHA : kHB;           // step s reads (s&1 ? HB : HA), writes the other
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int buf = q & 1;
+                const uint32_t G = tbase + lane_base + kG0 + buf * 128 + half * 16;
+                mbar_wait(bar(GATE_FULL0 + buf), full_phase[buf]);
+                full_phase[buf] ^= 1;
+                tc_fence_after();
+                uint32_t gi[16], gr[16], gz[16], gh[16];
+                tmem_ld16(G + 0, gi); tmem_ld16(G + 32, gr); tmem_ld16(G + 64, gz); tmem_ld16(G + 96, gh);
+                tc_wait_ld();
+                {   // re-zero the gh_n accumulator columns (the h-part MMAs always accumulate), then free the buffer
+                    uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    tmem_st8(G + 96, z8); tmem_st8(G + 96 + 8, z8);
+                    tc_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(bar(GATE_FREE0 + buf), 0);
+                }
+                const int u0 = q * 32 + half * 16;                // first hidden unit handled here
+                uint32_t phi[8], plo[8];
+                float hn[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int hid = u0 + j;
+                    float r = dr_sigmoid(__uint_as_float(gr[j]) + bs[hid]);
+                    float z = dr_sigmoid(__uint_as_float(gz[j]) + bs[DR_H + hid]);
+                    float n = dr_tanh(__uint_as_float(gi[j]) + bs[2 * DR_H + hid] + r * (__uint_as_float(gh[j]) + bs[3 * DR_H + hid]));
+                    float hold = hreg[q][j];
+                    float hnew = __fadd_rn(__fmul_rn(__fsub_rn(hold, n), z), n);   // (h - n)*z + n, as torch's CPU cell
+                    hreg[q][j] = hnew;
+                    hn[j] = hnew;
+                    o0 = fmaf(cs[hid], hnew, o0);
+                    o1 = fmaf(cs[DR_H + hid], hnew, o1);
+                    o2 = fmaf(cs[2 * DR_H + hid], hnew, o2);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    __nv_bfloat16 h0, l0, h1, l1;
+                    split_bf16(hn[2 * j], h0, l0);
+                    split_bf16(hn[2 * j + 1], h1, l1);
+                    phi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    plo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                tmem_st8(tbase + lane_base + hnext + u0 / 2, phi);
+                tmem_st8(tbase + lane_base + hnext + 64 + u0 / 2, plo);
+                if (live) {
+                    float* sp = S + (((size_t)tt * 64 + dir * 32 + u0 / 4) * Bp + b) * 4;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dr_red_add_v4(sp + (size_t)j * Bp * 4, hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar(H_READY), 0);
+            if (live) {
+                float* o = out_local + (((size_t)b * T + tt) * M_loc + e) * DR_Q;
+                dr_red_add(o, o0); dr_red_add(o + 1, o1); dr_red_add(o + 2, o2);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ======================= MMA issuer (leader CTA only) =======================
+        if (cta == 0 && elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(256, 96);
+            const uint32_t w_s = smem_u32(smem + kOffW);
+            const uint32_t x_s = smem_u32(smem + kOffX);
+            mbar_wait_cluster(bar(W_READY), 0);
+            uint32_t free_phase[2] = {0, 0};
+            for (int s = 0; s < T; ++s) {
+                const uint32_t hcur = tbase + ((s & 1) ? kHB : kHA);
+                const uint32_t xst = x_s + (s & 1) * kXStage;
+                mbar_wait_cluster(bar(X_FULL0 + (s & 1)), (s >> 1) & 1);
+                for (int q = 0; q < 4; ++q) {
+                    const int buf = q & 1;
+                    const uint32_t G = tbase + kG0 + buf * 128;
+                    const uint32_t wq = w_s + q * kQuarterBytes;
+                    mbar_wait_cluster(bar(GATE_FREE0 + buf), free_phase[buf]);
+                    free_phase[buf] ^= 1;
+                    tc_fence_after();
+                    // x-part: (hi,hi) (hi,lo) (lo,hi);  A parts at xst + {0, kXTile}, B parts at wq + {0, kBlk}
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t ab = xst + (term == 2 ? kXTile : 0);
+                        const uint32_t bb = wq + (term == 1 ? kBlk : 0);
+#pragma unroll
+                        for (int k16 = 0; k16 < 4; ++k16)
+                            mma_ss<2>(G, make_desc_sw128(ab + k16 * 32), make_desc_sw128(bb + k16 * 32), idesc,
+                                      (term | k16) ? 1u : 0u);
+                    }
+                    if (q == 0) { mbar_wait_cluster(bar(H_READY), s & 1); tc_fence_after(); }
+                    // h-part: A from TMEM (hi at hcur, lo at hcur+64), B blocks Wh_hi[kb] at wq+2*kBlk, Wh_lo[kb] at wq+4*kBlk
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t at = hcur + (term == 2 ? 64 : 0);
+                        const uint32_t bb = wq + (term == 1 ? 4 : 2) * kBlk;
+#pragma unroll
+                        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                            for (int k16 = 0; k16 < 4; ++k16)
+                                mma_ts<2>(G + 32, at + (kb * 64 + k16 * 16) / 2,
+                                          make_desc_sw128(bb + kb * kBlk + k16 * 32), idesc, 1u);
+                    }
+                    mma_commit_2(bar(GATE_FULL0 + buf), 0x3);
+                }
+                mma_commit_2(bar(X_FREE0 + (s & 1)), 0x3);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ======================= bulk-copy producer =======================
+        if (elect_one()) {
+            const uint8_t* wsrc = wtc + ((size_t)(e * 2 + dir) * 2 + cta) * kWBytes;
+            mbar_expect_tx(bar(W_LAND), kWBytes);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                bulk_g2s(smem_u32(smem + kOffW) + i * kQuarterBytes, wsrc + (size_t)i * kQuarterBytes, kQuarterBytes, bar(W_LAND));
+            bool w_pending = true;
+            for (int s = 0; s < T; ++s) {
+                const int st = s & 1;
+                const int tt = dir ? (T - 1 - s) : s;
+                if (s >= 2) mbar_wait(bar(X_FREE0 + st), ((s >> 1) - 1) & 1);
+                const uint8_t* xsrc = xtc + (((size_t)tt * ntiles + tile) * 2 + cta) * kXStage;
+                mbar_expect_tx(bar(X_LAND0 + st), kXStage);
+                bulk_g2s(smem_u32(smem + kOffX) + st * kXStage, xsrc, kXStage, bar(X_LAND0 + st));
+                if (w_pending) { mbar_wait(bar(W_LAND), 0); mbar_arrive_cluster(bar(W_READY), 0); w_pending = false; }
+                mbar_wait(bar(X_LAND0 + st), (s >> 1) & 1);
+                mbar_arrive_cluster(bar(X_FULL0 + st), 0);
+            }
+        }
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+}
+
+// ---- operand image builders -------------------------------------------------------------------
+
+// weights: one thread per (e, d, cta, q, block-kind kk in 0..2 (Wx, Wh kb0, Wh kb1), row48, chunk8)
+__global__ void dr_tc_pack_w_kernel(const float* __restrict__ blob, DrBlobOffsets off, int F,
+                                    const float* __restrict__ mask, uint8_t* __restrict__ wtc, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int chunk = (int)(i % 8); size_t r = i / 8;
+    int row = (int)(r % 48); r /= 48;
+    int kk = (int)(r % 3); r /= 3;
+    int q = (int)(r % 4); r /= 4;
+    int c = (int)(r % 2); r /= 2;
+    int d = (int)(r % 2); r /= 2;
+    int e = (int)r;
+    const float* ex = blob + (size_t)e * off.per_expert;
+    int col = c * 48 + row;                 // D column inside the 96-wide MMA
+    int grp = col / 32, unit = q * 32 + col % 32;
+    float v[8];
+    if (kk == 0) {                          // x-part rows: [gi_n | r | z]  -> torch gate index (2, 0, 1)
+        int gate = (grp == 0) ? 2 : grp - 1;
+        const float* w = ex + off.w_ih[d] + (size_t)(gate * DR_H + unit) * F;
+        for (int j = 0; j < 8; ++j) {
+            int k = chunk * 8 + j;
+            v[j] = (k < F) ? w[k] * mask[(size_t)e * F + k] : 0.0f;     // mask folded: W_ih' = W_ih diag(mask)
+        }
+    } else {                                // h-part rows: [r | z | gh_n] -> torch gate index (0, 1, 2)
+        const float* w = ex + off.w_hh[d] + (size_t)(grp * DR_H + unit) * DR_H + (kk - 1) * 64;
+        for (int j = 0; j < 8; ++j) v[j] = w[chunk * 8 + j];
+    }
+    uint32_t hi[4], lo[4];
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * j], h0, l0); split_bf16(v[2 * j + 1], h1, l1);
+        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    uint8_t* base = wtc + ((size_t)(e * 2 + d) * 2 + c) * kWBytes + (size_t)q * kQuarterBytes;
+    uint32_t hi_blk = (kk == 0) ? 0 : (kk == 1 ? 2 : 3);
+    uint32_t lo_blk = (kk == 0) ? 1 : (kk == 1 ? 4 : 5);
+    uint32_t o = sw128_offset(row, chunk * 8);
+    *reinterpret_cast<uint4*>(base + hi_blk * kBlk + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + lo_blk * kBlk + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// x [B,T,F] fp32 -> xtc [T][ntiles][2][hi|lo][128 rows x 64 K] swizzled bf16 images; zero padded
+__global__ void dr_tc_pack_x_kernel(const float* __restrict__ x, uint8_t* __restrict__ xtc,
+                                    int B, int T, int F, int ntiles) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)T * ntiles * 256 * 8;
+    if (i >= total) return;
+    int chunk = (int)(i % 8); size_t r = i / 8;
+    int rb = (int)(r % 256); r /= 256;
+    int tile = (int)(r % ntiles);
+    int t = (int)(r / ntiles);
+    int b = tile * 256 + rb;
+    float v[8];
+    for (int j = 0; j < 8; ++j) {
+        int f = chunk * 8 + j;
+        v[j] = (b < B && f < F) ? x[((size_t)b * T + t) * F + f] : 0.0f;
+    }
+    uint32_t hi[4], lo[4];
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * j], h0, l0); split_bf16(v[2 * j + 1], h1, l1);
+        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    int c = rb / 128, row = rb % 128;
+    uint8_t* base = xtc + (((size_t)t * ntiles + tile) * 2 + c) * kXStage;
+    uint32_t o = sw128_offset(row, chunk * 8);
+    *reinterpret_cast<uint4*>(base + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + kXTile + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+}  // namespace
+
+bool dr_tc_built() { return true; }
+
+bool dr_tc_supported(const dr_model* m, int B, int T) {
+    (void)B; (void)T;
+    return m->cfg.F <= 64;      // one 64-wide K block for the input projection (see header comment)
+}
+
+int dr_tc_prep_weights(dr_model* m) {
+    if (m->cfg.F > 64 || m->M_loc == 0) return DR_OK;
+    size_t bytes = (size_t)m->M_loc * 2 * 2 * kWBytes;
+    if (!m->d_wtc) {
+        DR_CUDA(m, cudaMalloc((void**)&m->d_wtc, bytes));
+        m->wtc_bytes = bytes;
+    }
+    size_t total = (size_t)m->M_loc * 2 * 2 * 4 * 3 * 48 * 8;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    dr_tc_pack_w_kernel<<<blocks, 256, 0, m->stream>>>(m->d_blob, m->off, m->cfg.F, m->d_mask,
+                                                       reinterpret_cast<uint8_t*>(m->d_wtc), total);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
+
+int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float* out_local) {
+    int ntiles = (B + 255) / 256;
+    int Bp = (B + 127) / 128 * 128;
+    size_t xbytes = (size_t)T * ntiles * 2 * kXStage;
+    int rc = dr_reserve(m, &m->d_xtc, &m->xtc_cap, xbytes);
+    if (rc != DR_OK) return rc;
+    {
+        size_t total = (size_t)T * ntiles * 256 * 8;
+        unsigned blocks = (unsigned)((total + 255) / 256);
+        dr_tc_pack_x_kernel<<<blocks, 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), B, T, m->cfg.F, ntiles);
+        DR_CUDA(m, cudaGetLastError());
+    }
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    int items = m->M_loc * 2 * ntiles;
+    cudaEvent_t* ev = dr_prof_slot(m);
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
+    dr_gru_tc_kernel<<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+        reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
+        S, out_local, B, T, Bp, m->M_loc, ntiles);
+    DR_CUDA(m, cudaGetLastError());
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
+    m->launches += 2;
+    return DR_OK;
 }

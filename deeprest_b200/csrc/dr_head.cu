@@ -9,21 +9,30 @@ namespace {
 
 constexpr int TM = 64, TN = 64, TK = 32, LD = 68;
 
+// grid (ceil(B/64), T, ceil(N/64)): a tile is 64 windows of one time step, so the k-group-major S
+// ([T][64][Bp][4]) is read as contiguous 1 KB runs.
 __global__ void __launch_bounds__(256)
 dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, const float* __restrict__ hb,
-               float* __restrict__ out, int R, int N) {
+               float* __restrict__ out, int B, int T, int BpS, int N) {
     __shared__ __align__(16) float As[TK][LD];
     __shared__ __align__(16) float Bs[TK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const size_t r0 = (size_t)blockIdx.x * TM;
-    const int c0 = blockIdx.y * TN;
+    const int b0 = blockIdx.x * TM;
+    const int t = blockIdx.y;
+    const int c0 = blockIdx.z * TN;
     float acc[4][4] = {};
     for (int k0 = 0; k0 < DR_2H; k0 += TK) {
 #pragma unroll
-        for (int i = 0; i < (TM * TK) / 256; ++i) {
+        for (int i = 0; i < (TM * TK / 4) / 256; ++i) {       // float4 loads: 64 rows x 8 k-groups
+            int idx = tid + i * 256, r = idx % TM, kg = idx / TM;
+            int b = b0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b < B) v = *reinterpret_cast<const float4*>(S + (((size_t)t * 64 + k0 / 4 + kg) * BpS + b) * 4);
+            As[kg * 4 + 0][r] = v.x; As[kg * 4 + 1][r] = v.y; As[kg * 4 + 2][r] = v.z; As[kg * 4 + 3][r] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < (TN * TK) / 256; ++i) {
             int idx = tid + i * 256, k = idx % TK, r = idx / TK;
-            size_t row = r0 + r;
-            As[k][r] = (row < (size_t)R) ? S[row * DR_2H + k0 + k] : 0.0f;
             int col = c0 + r;
             Bs[k][r] = (col < N) ? abar[(size_t)col * DR_2H + k0 + k] : 0.0f;
         }
@@ -42,12 +51,13 @@ dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, cons
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        size_t row = r0 + ty * 4 + i;
-        if (row >= (size_t)R) continue;
+        int b = b0 + ty * 4 + i;
+        if (b >= B) continue;
+        float* orow = out + ((size_t)b * T + t) * N;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int col = c0 + tx * 4 + j;
-            if (col < N) out[row * N + col] += acc[i][j] + hb[col];
+            if (col < N) orow[col] += acc[i][j] + hb[col];
         }
     }
 }
@@ -89,10 +99,10 @@ __global__ void dr_loss_final_kernel(const double* acc, double inv_n, float* los
 }  // namespace
 
 int dr_launch_heads(dr_model* m, const float* S, int B, int T, float* out_local) {
-    int R = B * T, N = m->M_loc * DR_Q;
+    int N = m->M_loc * DR_Q;
     if (N == 0) return DR_OK;
-    dim3 grid((R + TM - 1) / TM, (N + TN - 1) / TN);
-    dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, R, N);
+    dim3 grid((B + TM - 1) / TM, T, (N + TN - 1) / TN);
+    dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, B, T, dr_s_rows(B), N);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;

@@ -172,7 +172,7 @@ class QuantileRNN:
             _lib.check(self._h, self._lib.dr_forward_dev(self._h, x.data_ptr(), B, T, out.data_ptr()))
             return out
         import torch.distributed as dist
-        S = torch.empty((B, T, 2 * layout.H), device=x.device, dtype=torch.float32)
+        S = torch.empty((int(self._lib.dr_s_elems(B, T)),), device=x.device, dtype=torch.float32)
         out_local = torch.empty((B, T, self.m_local, layout.Q), device=x.device, dtype=torch.float32)
         _lib.check(self._h, self._lib.dr_forward_local_dev(self._h, x.data_ptr(), B, T, S.data_ptr(), out_local.data_ptr()))
         dist.all_reduce(S, op=dist.ReduceOp.SUM, group=self._pg)          # the one exchange step

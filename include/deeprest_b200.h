@@ -90,12 +90,15 @@ int  dr_forward    (dr_model* m, const float* x_host, int32_t B, int32_t T, floa
 int  dr_forward_dev(dr_model* m, const float* x_dev,  int32_t B, int32_t T, float* out_dev);
 
 /* ---- expert-sharded forward, device pointers, async ----
- *   1. dr_forward_local_dev : local bi-GRUs.  Writes S_dev[B,T,2H] = sum over LOCAL experts of
- *      their GRU outputs, and out_local_dev[B,T,M_loc,Q] = own-expert part of the heads.
+ *   1. dr_forward_local_dev : local bi-GRUs.  Writes S_dev = sum over LOCAL experts of their GRU
+ *      outputs (dr_s_elems(B,T) floats, stored k-group major [T][2H/4][round_up(B,128)][4]; the
+ *      layout is opaque to the caller, an element-wise all-reduce is all it needs), and
+ *      out_local_dev[B,T,M_loc,Q] = own-expert part of the heads.
  *   2. caller all-reduces (sum) S_dev across ranks (torch.distributed / NCCL).
  *   3. dr_forward_heads_dev : adds the cross-expert-mean term and bias into out_local_dev.
  *   4. caller all-gathers out_local into gathered[world][B,T,M_loc,Q];
  *      dr_interleave_dev reorders it to the reference layout out[B,T,M,Q] (qrnn.py:55). */
+int64_t dr_s_elems(int32_t B, int32_t T);     /* floats in S_dev for a [B,T] call */
 int  dr_forward_local_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T,
                           float* S_dev, float* out_local_dev);
 int  dr_forward_heads_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
@@ -111,8 +114,8 @@ int  dr_quantile_loss_dev(dr_model* m, const float* out_dev, const float* y_dev,
                           int32_t B, int32_t T, float* loss_dev);
 
 /* ---- test/diagnostic access to prepared tensors (not on the hot path) ----
- * what: "mask" [M_loc,F] (qrnn.py:34), "S" [B,T,2H] of the last forward, "launches" (1 int64
- * as float pair is NOT used; see dr_launch_count). Returns DR_EINVAL for unknown names. */
+ * what: "mask" [M_loc,F] (qrnn.py:34), "S" (dr_s_elems floats, layout above) of the last
+ * dr_forward/dr_forward_dev, "ct", "bias4". Returns DR_EINVAL for unknown names. */
 int  dr_debug_read(dr_model* m, const char* what, float* host_buf, size_t n_floats);
 /* per-kernel device timing (CUDA events on the launching stream). dr_profile(m,1) clears the
  * record and makes every forward (up to 256) record events around the recurrence kernel and the
@@ -120,6 +123,10 @@ int  dr_debug_read(dr_model* m, const char* what, float* host_buf, size_t n_floa
  * SUM of their kernel durations in milliseconds. */
 int  dr_profile(dr_model* m, int32_t enable);
 int  dr_profile_read(dr_model* m, int32_t* n_forwards, float* gru_ms_sum, float* head_ms_sum);
+/* hardware probe of the tensor-core building blocks (one tcgen05 GEMM tile; see
+ * csrc/dr_tc_probe.cu). variant bit0: A from TMEM, bit1: cta_group::2. Host pointers. */
+int  dr_tc_probe(int32_t variant, const void* a_host, size_t a_bytes, const void* b_host, size_t b_bytes,
+                 int32_t N, int32_t K, int32_t flags, float* d_out_host);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t dr_launch_count(const dr_model* m);
 /* name of the GRU engine the last forward used: "ffma" or "tcgen05" */

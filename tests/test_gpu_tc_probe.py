@@ -1,0 +1,78 @@
+"""Pins the tcgen05 building blocks the tensor-core GRU engine relies on (descriptor bits,
+SW128 K-major image, bulk copy, A-in-TMEM packing, cta_group::2 operand split, multicast
+commit, tcgen05.ld lane mapping) with one GEMM tile per variant, checked against numpy."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from deeprest_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_round(a):
+    """fp32 -> bf16 (round to nearest even) as uint16 bit patterns and the rounded fp32 values."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + 0x7FFF
+    b = ((u + r) >> 16).astype(np.uint16)
+    return b, (b.astype(np.uint32) << 16).view(np.float32)
+
+
+def sw128_image(bits):
+    """[rows, K] uint16 -> byte image [K/64][rows x 128 B], K-major 128B-swizzled (dr_tc.cuh::sw128_offset)."""
+    rows, K = bits.shape
+    assert rows % 8 == 0 and K % 64 == 0
+    img = np.zeros((K // 64, rows * 64), np.uint16)
+    r = np.arange(rows)[:, None]
+    k = np.arange(64)[None, :]
+    off = (r // 8) * 1024 + (r % 8) * 128 + (((k // 8) ^ (r % 8)) * 16) + (k % 8) * 2
+    for kb in range(K // 64):
+        img[kb, off // 2] = bits[:, kb * 64:(kb + 1) * 64]
+    return img
+
+
+def run_probe(variant, A, B, flags=0):
+    lib = _lib.load()
+    cg = 2 if variant & 2 else 1
+    N, K = B.shape
+    a_bits, a_val = bf16_round(A)
+    b_bits, b_val = bf16_round(B)
+    if variant & 1:
+        a_buf = np.ascontiguousarray(a_bits)
+    else:
+        a_buf = np.ascontiguousarray(np.stack([sw128_image(a_bits[c * 128:(c + 1) * 128]) for c in range(cg)]))
+    nloc = N // cg
+    b_buf = np.ascontiguousarray(np.stack([sw128_image(b_bits[c * nloc:(c + 1) * nloc]) for c in range(cg)]))
+    out = np.zeros((cg * 128, N), np.float32)
+    rc = lib.dr_tc_probe(variant, a_buf.ctypes.data, a_buf.nbytes, b_buf.ctypes.data, b_buf.nbytes,
+                         N, K, flags, out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0, lib.dr_last_error(None)
+    ref = a_val.astype(np.float64) @ b_val.astype(np.float64).T
+    return out, ref
+
+
+@pytest.mark.parametrize("variant,name", [(0, "SS cta_group::1"), (1, "TS cta_group::1"),
+                                           (2, "SS cta_group::2"), (3, "TS cta_group::2")])
+@pytest.mark.parametrize("N,K", [(96, 64), (96, 128), (256, 128), (32, 192)])
+def test_tcgen05_tile(variant, name, N, K):
+    rng = np.random.default_rng(variant * 100 + N + K)
+    cg = 2 if variant & 2 else 1
+    A = rng.standard_normal((cg * 128, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    out, ref = run_probe(variant, A, B)
+    err = np.abs(out - ref).max()
+    print(f"{name} N={N} K={K}: max err {err:.3e}")
+    if err > 1e-3:
+        # diagnostics: which hypothesis would have matched?
+        hints = []
+        if variant & 1:
+            o2, _ = run_probe(variant, A, B, flags=1)
+            hints.append(f"swapped bf16 halves -> {np.abs(o2 - ref).max():.3e}")
+        if cg == 2:
+            for perm_name, cols in [("B halves swapped", np.r_[N // 2:N, 0:N // 2])]:
+                hints.append(f"{perm_name} -> {np.abs(out - ref[:, cols]).max():.3e}")
+            hints.append(f"rows swapped -> {np.abs(out - ref[np.r_[128:256, 0:128]]).max():.3e}")
+        np.save(f"gpurun_out/probe_v{variant}_N{N}_K{K}_out.npy", out)
+        np.save(f"gpurun_out/probe_v{variant}_N{N}_K{K}_ref.npy", ref)
+        pytest.fail(f"{name} N={N} K={K}: max err {err:.3e}; " + "; ".join(hints))
