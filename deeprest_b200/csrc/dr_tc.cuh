@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace drtc {
@@ -149,6 +150,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          | ((uint32_t)(M >> 4) << 24);   // M / 16
 }
 
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major (format code 0 = F16)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // byte offset of element (row, k) inside a [rows x 64] bf16 SW128 K-major block (block base 1024 B aligned)
 __host__ __device__ inline uint32_t sw128_offset(int row, int k) {
     uint32_t chunk = (uint32_t)(k >> 3) ^ (uint32_t)(row & 7);
@@ -159,6 +165,18 @@ __host__ __device__ inline uint32_t sw128_offset(int row, int k) {
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// fp32 -> (hi, lo) fp16 split: hi = rn(v), lo = rn(v - hi).  v ~= hi + lo to 2^-22 relative (or 2^-25
+// absolute once lo falls into the fp16 subnormals) — 64x tighter than the bf16 pair for O(0.1..1) values,
+// which are the ones that set the absolute error of a gate pre-activation.  |v| is clamped to the fp16 range.
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+    v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
 }  // namespace drtc

@@ -69,7 +69,7 @@ dr_tc_probe_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
 
     if (warp == 4 && cta == 0) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128 * CG, N);
+            const uint32_t idesc = (flags & 2) ? make_idesc_f16(128 * CG, N) : make_idesc_bf16(128 * CG, N);
             uint32_t acc = 0;
             for (int kb = 0; kb < KB; ++kb)
                 for (int k16 = 0; k16 < 4; ++k16) {
@@ -125,7 +125,8 @@ int run_probe(const uint8_t* a, const uint8_t* b, int N, int K, int flags, float
 
 }  // namespace
 
-// variant: bit0 = A from TMEM (TS), bit1 = cta_group::2.  flags bit0: swap the bf16 halves when packing A.
+// variant: bit0 = A from TMEM (TS), bit1 = cta_group::2.  flags bit0: swap the 16-bit halves when packing A;
+// flags bit1: operands are fp16 instead of bf16.
 // a: SS -> swizzled image [CG][K/64][128 rows x 128 B]; TS -> raw bf16 [CG*128][K].
 // b: swizzled image [CG][K/64][N/CG rows x 128 B].   d_out: fp32 [CG*128][N] (host).
 extern "C" int dr_tc_probe(int32_t variant, const void* a_host, size_t a_bytes, const void* b_host, size_t b_bytes,

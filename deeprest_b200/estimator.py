@@ -171,17 +171,21 @@ class QuantileRNN:
             out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
             _lib.check(self._h, self._lib.dr_forward_dev(self._h, x.data_ptr(), B, T, out.data_ptr()))
             return out
-        import torch.distributed as dist
-        S = torch.empty((int(self._lib.dr_s_elems(B, T)),), device=x.device, dtype=torch.float32)
-        out_local = torch.empty((B, T, self.m_local, layout.Q), device=x.device, dtype=torch.float32)
-        _lib.check(self._h, self._lib.dr_forward_local_dev(self._h, x.data_ptr(), B, T, S.data_ptr(), out_local.data_ptr()))
-        dist.all_reduce(S, op=dist.ReduceOp.SUM, group=self._pg)          # the one exchange step
-        _lib.check(self._h, self._lib.dr_forward_heads_dev(self._h, S.data_ptr(), B, T, out_local.data_ptr()))
-        gathered = torch.empty((self.world, B, T, self.m_local, layout.Q), device=x.device, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, out_local, group=self._pg)
-        out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
-        _lib.check(self._h, self._lib.dr_interleave_dev(self._h, gathered.data_ptr(), B, T, out.data_ptr()))
-        return out
+        from .sharding import sharded_forward
+        lib, h = self._lib, self._h
+
+        def local_fn(xx, S, out_local):
+            _lib.check(h, lib.dr_forward_local_dev(h, xx.data_ptr(), B, T, S.data_ptr(), out_local.data_ptr()))
+
+        def heads_fn(S, out_local):
+            _lib.check(h, lib.dr_forward_heads_dev(h, S.data_ptr(), B, T, out_local.data_ptr()))
+
+        def interleave_fn(gathered, out):
+            _lib.check(h, lib.dr_interleave_dev(h, gathered.data_ptr(), B, T, out.data_ptr()))
+
+        return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
+                               s_elems=lib.dr_s_elems(B, T), local_fn=local_fn, heads_fn=heads_fn,
+                               interleave_fn=interleave_fn, group=self._pg)
 
     # ---- loss ------------------------------------------------------------------------
     def quantile_loss(self, outputs, labels):

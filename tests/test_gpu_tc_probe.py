@@ -32,12 +32,18 @@ def sw128_image(bits):
     return img
 
 
+def f16_round(a):
+    h = np.ascontiguousarray(a, np.float32).astype(np.float16)
+    return h.view(np.uint16), h.astype(np.float32)
+
+
 def run_probe(variant, A, B, flags=0):
     lib = _lib.load()
     cg = 2 if variant & 2 else 1
     N, K = B.shape
-    a_bits, a_val = bf16_round(A)
-    b_bits, b_val = bf16_round(B)
+    rnd = f16_round if flags & 2 else bf16_round
+    a_bits, a_val = rnd(A)
+    b_bits, b_val = rnd(B)
     if variant & 1:
         a_buf = np.ascontiguousarray(a_bits)
     else:
@@ -50,6 +56,16 @@ def run_probe(variant, A, B, flags=0):
     assert rc == 0, lib.dr_last_error(None)
     ref = a_val.astype(np.float64) @ b_val.astype(np.float64).T
     return out, ref
+
+
+def test_tcgen05_tile_fp16_operands():
+    """the GRU engine's operand format: fp16 x fp16 -> fp32 (idesc format code 0), 2-CTA, A from TMEM"""
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((256, 128)).astype(np.float32)
+    B = rng.standard_normal((96, 128)).astype(np.float32)
+    for variant in (2, 3):
+        out, ref = run_probe(variant, A, B, flags=2)
+        assert np.abs(out - ref).max() < 1e-3, (variant, np.abs(out - ref).max())
 
 
 @pytest.mark.parametrize("variant,name", [(0, "SS cta_group::1"), (1, "TS cta_group::1"),
