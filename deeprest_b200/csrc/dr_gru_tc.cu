@@ -32,6 +32,7 @@ using namespace drtc;
 namespace {
 
 constexpr int kThreads = 320;
+constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = 8, kLoadWarp = 9;
 constexpr uint32_t kBlk = 48 * 128;                 // one B block: 48 rows x 64 K (bf16) = 6 KB
@@ -49,8 +50,23 @@ constexpr uint32_t kOffCt = kOffBias + 4 * DR_H * 4;        // Q*H floats
 constexpr uint32_t kOffBar = kOffCt + DR_Q * DR_H * 4;      // barriers
 constexpr uint32_t kSmemBytes = kOffBar + 256;
 
-enum Bar { GATE_FULL0 = 0, GATE_FULL1, GATE_FREE0, GATE_FREE1, H_READY, X_FULL0, X_FULL1, X_FREE0, X_FREE1,
+enum Bar { GATE_FULL0 = 0, GATE_FULL1, GATE_FREE0, GATE_FREE1, H_READY0, H_READY1, H_READY2, H_READY3,
+           X_FULL0, X_FULL1, X_FREE0, X_FREE1,
            X_LAND0, X_LAND1, W_LAND, W_READY, NUM_BARS };
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 16 fp32 values from shared memory -> this warp's lanes x 16 TMEM columns (every lane stores the same row of constants)
+__device__ __forceinline__ void store_bhn(uint32_t taddr, const float* src) {
+    const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+    const float4 c = *reinterpret_cast<const float4*>(src + 8), d = *reinterpret_cast<const float4*>(src + 12);
+    uint32_t v0[8] = {__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(a.z), __float_as_uint(a.w),
+                      __float_as_uint(b.x), __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w)};
+    uint32_t v1[8] = {__float_as_uint(c.x), __float_as_uint(c.y), __float_as_uint(c.z), __float_as_uint(c.w),
+                      __float_as_uint(d.x), __float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(d.w)};
+    tmem_st8(taddr, v0);
+    tmem_st8(taddr + 8, v1);
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][kWBytes]
@@ -74,12 +90,17 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
 
-    for (int i = tid; i < 4 * DR_H; i += kThreads) bs[i] = bias4[(size_t)(e * 2 + dir) * 4 * DR_H + i];
+    // gate constants, pre-scaled for ex2:  [0] -(b_ir+b_hr)*log2e   [1] -(b_iz+b_hz)*log2e   [2] 2*log2e*b_in   [3] b_hn
+    for (int i = tid; i < 4 * DR_H; i += kThreads) {
+        float v = bias4[(size_t)(e * 2 + dir) * 4 * DR_H + i];
+        int c = i / DR_H;
+        bs[i] = (c < 2) ? -v * kLog2e : (c == 2) ? 2.0f * kLog2e * v : v;
+    }
     for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i];
     if (tid == 0) {
         mbar_init(bar(GATE_FULL0), 1); mbar_init(bar(GATE_FULL1), 1);
         mbar_init(bar(GATE_FREE0), 2 * kEpiWarps); mbar_init(bar(GATE_FREE1), 2 * kEpiWarps);
-        mbar_init(bar(H_READY), 2 * kEpiWarps);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(H_READY0 + i), 2 * kEpiWarps);
         mbar_init(bar(X_FULL0), 2); mbar_init(bar(X_FULL1), 2);
         mbar_init(bar(X_FREE0), 1); mbar_init(bar(X_FREE1), 1);
         mbar_init(bar(X_LAND0), 1); mbar_init(bar(X_LAND1), 1);
@@ -100,25 +121,28 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
         const int b = tile * 256 + (int)cta * 128 + row;
         const bool live = b < B;
 
-        // ---- init: h0 = 0 (qrnn.py:39), gh_n accumulator columns = 0, then publish "previous step done"
+        // ---- init: h0 = 0 (qrnn.py:39), gh_n accumulator columns = b_hn, then publish "previous step done"
         {
             uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int c = 0; c < 64; c += 8) tmem_st8(tbase + lane_base + kHA + half * 64 + c, z8);
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                tmem_st8(tbase + lane_base + kG0 + g * 128 + 96 + half * 16, z8);
-                tmem_st8(tbase + lane_base + kG0 + g * 128 + 96 + half * 16 + 8, z8);
-            }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive_cluster(bar(H_READY), 0);
-                mbar_arrive_cluster(bar(GATE_FREE0), 0);
-                mbar_arrive_cluster(bar(GATE_FREE1), 0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mbar_arrive_remote(bar(H_READY0 + i), 0);
             }
         }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            // buffer g serves quarters g and g+2; the first use is quarter g
+            store_bhn(tbase + lane_base + kG0 + g * 128 + 96 + half * 16, bs + 3 * DR_H + g * 32 + half * 16);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_remote(bar(GATE_FREE0), 0); mbar_arrive_remote(bar(GATE_FREE1), 0); }
 
         float hreg[4][16];
 #pragma unroll
@@ -134,6 +158,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int buf = q & 1;
+                const int u0 = q * 32 + half * 16;                // first hidden unit handled here
                 const uint32_t G = tbase + lane_base + kG0 + buf * 128 + half * 16;
                 mbar_wait(bar(GATE_FULL0 + buf), full_phase[buf]);
                 full_phase[buf] ^= 1;
@@ -141,41 +166,72 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 uint32_t gi[16], gr[16], gz[16], gh[16];
                 tmem_ld16(G + 0, gi); tmem_ld16(G + 32, gr); tmem_ld16(G + 64, gz); tmem_ld16(G + 96, gh);
                 tc_wait_ld();
-                {   // re-zero the gh_n accumulator columns (the h-part MMAs always accumulate), then free the buffer
-                    uint32_t z8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                    tmem_st8(G + 96, z8); tmem_st8(G + 96 + 8, z8);
+                {   // re-arm the gh_n accumulator columns with b_hn of the quarter that uses this buffer next
+                    // (the h-part MMAs always accumulate), then hand the buffer back to the MMA warp
+                    const int qn = (q + 2) & 3;
+                    store_bhn(G + 96, bs + 3 * DR_H + qn * 32 + half * 16);
                     tc_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(bar(GATE_FREE0 + buf), 0);
+                    if (lane == 0) mbar_arrive_remote(bar(GATE_FREE0 + buf), 0);
                 }
-                const int u0 = q * 32 + half * 16;                // first hidden unit handled here
                 uint32_t phi[8], plo[8];
                 float hn[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int hid = u0 + j;
-                    float r = dr_sigmoid(__uint_as_float(gr[j]) + bs[hid]);
-                    float z = dr_sigmoid(__uint_as_float(gz[j]) + bs[DR_H + hid]);
-                    float n = dr_tanh(__uint_as_float(gi[j]) + bs[2 * DR_H + hid] + r * (__uint_as_float(gh[j]) + bs[3 * DR_H + hid]));
-                    float hold = hreg[q][j];
-                    float hnew = __fadd_rn(__fmul_rn(__fsub_rn(hold, n), z), n);   // (h - n)*z + n, as torch's CPU cell
-                    hreg[q][j] = hnew;
-                    hn[j] = hnew;
-                    o0 = fmaf(cs[hid], hnew, o0);
-                    o1 = fmaf(cs[DR_H + hid], hnew, o1);
-                    o2 = fmaf(cs[2 * DR_H + hid], hnew, o2);
-                }
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const float4 cr = *reinterpret_cast<const float4*>(bs + u0 + j4);
+                    const float4 cz = *reinterpret_cast<const float4*>(bs + DR_H + u0 + j4);
+                    const float4 cn = *reinterpret_cast<const float4*>(bs + 2 * DR_H + u0 + j4);
+                    const float4 h0c = *reinterpret_cast<const float4*>(cs + u0 + j4);
+                    const float4 h1c = *reinterpret_cast<const float4*>(cs + DR_H + u0 + j4);
+                    const float4 h2c = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0 + j4);
+                    const float crv[4] = {cr.x, cr.y, cr.z, cr.w}, czv[4] = {cz.x, cz.y, cz.z, cz.w};
+                    const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
+                    const float c0v[4] = {h0c.x, h0c.y, h0c.z, h0c.w}, c1v[4] = {h1c.x, h1c.y, h1c.z, h1c.w};
+                    const float c2v[4] = {h2c.x, h2c.y, h2c.z, h2c.w};
+                    float rr[4], zz[4], pn[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    __half h0, l0, h1, l1;
-                    split_f16(hn[2 * j], h0, l0);
-                    split_f16(hn[2 * j + 1], h1, l1);
-                    phi[j] = pack_h2(h0, h1);
-                    plo[j] = pack_h2(l0, l1);
+                    for (int i = 0; i < 4; ++i) {
+                        const int j = j4 + i;
+                        // r, z = sigmoid(.) with ONE shared reciprocal: 1/((1+er)(1+ez))
+                        float er = ex2_approx(fminf(fmaf(__uint_as_float(gr[j]), -kLog2e, crv[i]), 40.0f));
+                        float ez = ex2_approx(fminf(fmaf(__uint_as_float(gz[j]), -kLog2e, czv[i]), 40.0f));
+                        float pr = 1.0f + er, pz = 1.0f + ez;
+                        float inv = rcp_approx(pr * pz);
+                        rr[i] = pz * inv;
+                        zz[i] = pr * inv;
+                        // n = tanh(gi_n + b_in + r*(gh_n + b_hn)) = 1 - 2/(1 + exp(2t));  b_hn is already in gh
+                        float t = fmaf(rr[i], __uint_as_float(gh[j]), __uint_as_float(gi[j]));
+                        pn[i] = 1.0f + ex2_approx(fminf(fmaf(t, 2.0f * kLog2e, cnv[i]), 40.0f));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i += 2) {                  // tanh pairs share a reciprocal
+                        const int j = j4 + i;
+                        float inv = rcp_approx(pn[i] * pn[i + 1]);
+                        float n0 = fmaf(-2.0f * pn[i + 1], inv, 1.0f);
+                        float n1 = fmaf(-2.0f * pn[i], inv, 1.0f);
+                        // h' = (1-z)*n + z*h, evaluated as torch's CPU cell does: (h - n)*z + n
+                        float a0 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j], n0), zz[i]), n0);
+                        float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
+                        hreg[q][j] = a0; hreg[q][j + 1] = a1;
+                        hn[j] = a0; hn[j + 1] = a1;
+                        o0 = fmaf(c0v[i], a0, o0); o0 = fmaf(c0v[i + 1], a1, o0);
+                        o1 = fmaf(c1v[i], a0, o1); o1 = fmaf(c1v[i + 1], a1, o1);
+                        o2 = fmaf(c2v[i], a0, o2); o2 = fmaf(c2v[i + 1], a1, o2);
+                        // fp16 split of the pair with packed conversions (F2FP / HADD2.F32: no XU-pipe traffic)
+                        __half2 hi2 = __floats2half2_rn(a0, a1);
+                        float2 back = __half22float2(hi2);
+                        __half2 lo2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
+                        phi[j >> 1] = *reinterpret_cast<uint32_t*>(&hi2);
+                        plo[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
+                    }
                 }
                 tmem_st8(tbase + lane_base + hnext + u0 / 2, phi);
                 tmem_st8(tbase + lane_base + hnext + 64 + u0 / 2, plo);
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(bar(H_READY0 + q), 0);   // K columns [32q, 32q+32) of h_t are in TMEM
                 if (live) {
                     float* sp = S + (((size_t)tt * 64 + dir * 32 + u0 / 4) * Bp + b) * 4;
 #pragma unroll
@@ -183,10 +239,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         dr_red_add_v4(sp + (size_t)j * Bp * 4, hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
                 }
             }
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar(H_READY), 0);
             if (live) {
                 float* o = out_local + (((size_t)b * T + tt) * M_loc + e) * DR_Q;
                 dr_red_add(o, o0); dr_red_add(o + 1, o1); dr_red_add(o + 2, o2);
@@ -221,18 +273,24 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                             mma_ss<2>(G, make_desc_sw128(ab + k16 * 32), make_desc_sw128(bb + k16 * 32), idesc,
                                       (term | k16) ? 1u : 0u);
                     }
-                    if (q == 0) { mbar_wait_cluster(bar(H_READY), s & 1); tc_fence_after(); }
-                    // h-part: A from TMEM (hi at hcur, lo at hcur+64), B blocks Wh_hi[kb] at wq+2*kBlk, Wh_lo[kb] at wq+4*kBlk
+                    // h-part: A from TMEM (hi at hcur, lo at hcur+64), B blocks Wh_hi[kb] at wq+2*kBlk, Wh_lo[kb] at wq+4*kBlk.
+                    // K is walked in quarters of 32: quarter kq of h_{t-1} is published by the epilogue as soon as
+                    // hidden quarter kq is done, so only the last 6 MMAs of the step's first quarter wait for the
+                    // end of the previous step's epilogue.
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t at = hcur + (term == 2 ? 64 : 0);
-                        const uint32_t bb = wq + (term == 1 ? 4 : 2) * kBlk;
+                    for (int kq = 0; kq < 4; ++kq) {
+                        if (q == 0) { mbar_wait_cluster(bar(H_READY0 + kq), s & 1); tc_fence_after(); }
 #pragma unroll
-                        for (int kb = 0; kb < 2; ++kb)
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t at = hcur + (term == 2 ? 64 : 0);
+                            const uint32_t bb = wq + (term == 1 ? 4 : 2) * kBlk;
 #pragma unroll
-                            for (int k16 = 0; k16 < 4; ++k16)
+                            for (int j = 0; j < 2; ++j) {
+                                const int ks = kq * 2 + j, kb = ks >> 2, k16 = ks & 3;
                                 mma_ts<2>(G + 32, at + (kb * 64 + k16 * 16) / 2,
                                           make_desc_sw128(bb + kb * kBlk + k16 * 32), idesc, 1u);
+                            }
+                        }
                     }
                     mma_commit_2(bar(GATE_FULL0 + buf), 0x3);
                 }

@@ -36,6 +36,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
                  "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
                  :: "r"(bar), "r"(rank) : "memory");
 }
+// same, default semantics (.release at CTA scope): no GPU-scope MEMBAR in front of the arrive.  Used where the
+// barrier only orders tcgen05/TMEM traffic (ordered by tcgen05.fence + the arrive itself), so that outstanding
+// global REDs of the arriving warp need not drain first (ncu r01a: MEMBAR.ALL.GPU/ERRBAR = 25% of all stall samples).
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+                 :: "r"(bar), "r"(rank) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -172,6 +180,11 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
 // which are the ones that set the absolute error of a gate pre-activation.  |v| is clamped to the fp16 range.
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
     v = fminf(fmaxf(v, -65504.0f), 65504.0f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+// same without the range clamp (for values known to be in (-1, 1): the GRU state)
+__device__ __forceinline__ void split_f16_unit(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
