@@ -1,0 +1,64 @@
+"""Expert-sharded forward on 2 GPUs over NCCL (skipped on a 1-GPU box): the sharded result on every
+rank must match the single-GPU result of the same model and the oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+M, B, T, F = 8, 300, 24, 32
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, path, engine):
+    import torch
+    import torch.distributed as dist
+    from deeprest_b200 import QuantileRNN, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        m_loc = M // world
+        blob = synth.weights(31, M, F, 1.5, experts=(rank * m_loc, (rank + 1) * m_loc))   # only the local shard
+        x = torch.from_numpy(synth.windows(5, B, T, F, "diurnal")).cuda()
+        model = QuantileRNN(F, M, engine=engine, device=rank, process_group=dist.group.WORLD).eval()
+        model.load_blob(blob)
+        out = model(x)
+        torch.cuda.synchronize()
+        np.save(f"{path}.{rank}.npy", out.cpu().numpy())
+        model.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "ffma"])
+def test_two_gpu_sharded_forward_matches_single_gpu(tmp_path, engine):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deeprest_b200 import QuantileRNN, synth
+    from oracle import qrnn_numpy as oracle
+    path = str(tmp_path / "out")
+    mp.spawn(_worker, args=(2, _free_port(), path, engine), nprocs=2, join=True)
+    blob = synth.weights(31, M, F, 1.5)
+    x = synth.windows(5, B, T, F, "diurnal")
+    single = QuantileRNN(F, M, engine=engine).eval()
+    single.load_blob(blob)
+    ref1 = single(x)
+    single.close()
+    ref = oracle.forward(blob, x[:6], M, F)
+    for r in range(2):
+        out = np.load(f"{path}.{r}.npy")
+        assert out.shape == (B, T, M, 3)
+        assert np.abs(out - ref1).max() < 2e-6, f"rank {r} vs single GPU: {np.abs(out - ref1).max()}"
+        assert np.all(np.abs(out[:6] - ref) <= 1e-6 + 1e-4 * np.abs(ref))
