@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -88,7 +88,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[:getattr(self, "stop_at", None)]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except (ValueError, IndexError):
@@ -273,12 +273,15 @@ def run_ours(args, rank, world, local_rank):
     launches0 = model.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
+        time.sleep(0.15)                      # let nvidia-smi start; the loop below is what it samples
         barrier()
+        clocks.rows.clear()
         ev0.record()
         for _ in range(args.steps):
             out = model(x_dev)
         ev1.record()
         barrier()
+        clocks.stop_at = len(clocks.rows)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     launches = model.launch_count - launches0
     n_prof, gru_ms_sum, head_ms_sum = model.profile_read()
