@@ -78,6 +78,8 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->stream = nullptr; m->own_stream = nullptr;
     m->d_blob = m->d_mask = m->d_wf = m->d_bias4 = m->d_ct = m->d_abar = m->d_hb = nullptr;
     m->d_wtc = nullptr; m->wtc_bytes = 0;
+    m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
+    m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
     m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
@@ -94,6 +96,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->stream = m->own_stream;
     alloc(&m->d_blob, Ml * m->off.per_expert);
     alloc(&m->d_mask, Ml * cfg->F);
+    alloc(&m->d_wihm, 2 * Ml * 3 * DR_H * cfg->F);
     alloc(&m->d_wf, Ml * 2 * 2 * KT * 3 * 64);
     alloc(&m->d_bias4, Ml * 2 * 4 * DR_H);
     alloc(&m->d_ct, Ml * 2 * DR_Q * DR_H);
@@ -109,7 +112,8 @@ void dr_destroy(dr_model* m) {
     if (!m) return;
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
-    void* ptrs[] = {m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+    dr_train_free(m);
+    void* ptrs[] = {m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->d_xT, m->d_xtc, m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);

@@ -53,6 +53,11 @@ struct dr_model {
     float* d_ct;                    // own-expert head coeff C - A/(M-1)      [M_loc,2,Q,H]
     float* d_abar;                  // mean-term head coeff A/(M-1)           [M_loc*Q, 2H]
     float* d_hb;                    // head bias                              [M_loc*Q]
+    float* d_wihm;                  // mask-folded input weights W_ih*diag(mask)   [2][M_loc][3H][F] (training GEMM)
+    float* d_grad;                  // gradients of the last train step, reference blob order [M_loc*per_expert]
+    float* d_adam_m; float* d_adam_v; int64_t adam_step;
+    void*  train_ws;                // training workspace (dr_train.cu)
+    void*  d_dropmask; size_t dropmask_cap;
     __nv_bfloat16* d_wtc;           // tcgen05 weight image (hi/lo bf16)      see dr_gru_tc.cu
     size_t wtc_bytes;
 
@@ -109,6 +114,10 @@ bool dr_tc_built();
 bool dr_tc_supported(const dr_model* m, int B, int T);
 int dr_tc_prep_weights(dr_model* m);
 int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev, float* out_local_dev);
+// dr_train.cu
+int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
+                       float lr, float* loss_dev, float* out_dev);
+void dr_train_free(dr_model* m);
 // dr_head.cu
 int dr_launch_heads(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 int dr_launch_interleave(dr_model* m, const float* gathered, int B, int T, float* out);

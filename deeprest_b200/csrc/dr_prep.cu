@@ -87,6 +87,17 @@ __global__ void dr_pack_small_kernel(const float* __restrict__ blob, DrBlobOffse
     if (threadIdx.x < DR_Q) hb[e * DR_Q + threadIdx.x] = ex[off.head_b + threadIdx.x];
 }
 
+// wihm[d][e][i][f] = W_ih[d][e][i][f] * mask[e][f]   (training-path input projection, same folding as inference)
+__global__ void dr_pack_wihm_kernel(const float* __restrict__ blob, DrBlobOffsets off, int F, int M_loc,
+                                    const float* __restrict__ mask, float* __restrict__ wihm, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int f = (int)(i % F); size_t r = i / F;
+    int row = (int)(r % (3 * DR_H)); r /= 3 * DR_H;
+    int e = (int)(r % M_loc); int d = (int)(r / M_loc);
+    wihm[i] = blob[(size_t)e * off.per_expert + off.w_ih[d] + (size_t)row * F + f] * mask[(size_t)e * F + f];
+}
+
 int dr_launch_prep(dr_model* m) {
     int F = m->cfg.F, Fp = m->Fp, Ml = m->M_loc;
     if (Ml == 0) return DR_OK;
@@ -97,10 +108,15 @@ int dr_launch_prep(dr_model* m) {
     unsigned blocks = (unsigned)((total + 255) / 256);
     dr_pack_ffma_kernel<<<blocks, 256, 0, m->stream>>>(m->d_blob, m->off, F, Fp, m->d_mask, m->d_wf, total);
     DR_CUDA(m, cudaGetLastError());
+    {
+        size_t tw = (size_t)2 * Ml * 3 * DR_H * F;
+        dr_pack_wihm_kernel<<<(unsigned)((tw + 255) / 256), 256, 0, m->stream>>>(m->d_blob, m->off, F, Ml, m->d_mask, m->d_wihm, tw);
+        DR_CUDA(m, cudaGetLastError());
+    }
     float inv_m1 = 1.0f / (float)(m->cfg.M - 1);
     dr_pack_small_kernel<<<Ml, 256, 0, m->stream>>>(m->d_blob, m->off, Ml, inv_m1, m->d_bias4, m->d_ct,
                                                     m->d_abar, m->d_hb);
     DR_CUDA(m, cudaGetLastError());
-    m->launches += 3;
+    m->launches += 4;
     return DR_OK;
 }

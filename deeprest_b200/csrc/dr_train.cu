@@ -1,0 +1,626 @@
+// Training step of the estimator (estimate.py:67-74): forward in train mode (dropout on the GRU
+// outputs, qrnn.py:43), pinball loss (qrnn.py:58-67), the backward that torch autograd derives
+// from qrnn.py:28-67 (adjoints listed in SURVEY §8a "Backward"), and Adam (estimate.py:61).
+//
+// Round-1 implementation: exact fp32 on the CUDA cores, organised as batched GEMMs + fused
+// elementwise kernels in TIME-MAJOR activations (row = t*Bm + b), one launch per time step and
+// direction for the recurrence.  It is the parity-complete training path (gradients of every
+// parameter family match the reference's autograd); moving its GEMMs to tcgen05 is later work.
+// Memory: 4.5 KB per expert-window-step-direction, so large batches are processed in micro-batches
+// of Bm windows (exact: windows are independent given the cross-expert sums, and gradients add).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include "dr_common.cuh"
+
+namespace {
+
+constexpr int GT = 64, GK = 16, GLD = GT + 4;
+
+// C[z](m,n) = beta*C[z](m,n) + sum_k A[z](m,k) * B[z](k,n), arbitrary element strides
+struct Gemm {
+    const float* A; const float* B; float* C;
+    int M, N, K;
+    long sam, sak, sbk, sbn, scm, scn;
+    long bsA, bsB, bsC;
+    float beta;
+};
+
+__global__ void __launch_bounds__(256) dr_bgemm_kernel(Gemm g) {
+    __shared__ __align__(16) float As[GK][GLD];
+    __shared__ __align__(16) float Bs[GK][GLD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    const float* A = g.A + (size_t)blockIdx.z * g.bsA;
+    const float* B = g.B + (size_t)blockIdx.z * g.bsB;
+    float* C = g.C + (size_t)blockIdx.z * g.bsC;
+    const bool a_m_fast = g.sam <= g.sak, b_n_fast = g.sbn <= g.sbk;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < g.K; k0 += GK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int idx = tid + i * 256;
+            int m = a_m_fast ? idx % GT : idx / GK, k = a_m_fast ? idx / GT : idx % GK;
+            As[k][m] = (m0 + m < g.M && k0 + k < g.K) ? A[(long)(m0 + m) * g.sam + (long)(k0 + k) * g.sak] : 0.0f;
+            int n = b_n_fast ? idx % GT : idx / GK, kb = b_n_fast ? idx / GT : idx % GK;
+            Bs[kb][n] = (n0 + n < g.N && k0 + kb < g.K) ? B[(long)(k0 + kb) * g.sbk + (long)(n0 + n) * g.sbn] : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float* c = C + (long)m * g.scm + (long)n * g.scn;
+            *c = (g.beta == 0.0f) ? acc[i][j] : g.beta * *c + acc[i][j];
+        }
+    }
+}
+
+// ---- dropout keep decision: replayed mask (parity) or counter-based hash (production) -------------
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// idx = ((e_glob*B + b)*T + t)*2H + k   — the reference's rnn_out element order [M,B,T,2H]
+__device__ __forceinline__ float keep_scale(const uint8_t* mask, uint64_t seed, size_t idx, float p, float inv_keep) {
+    if (mask) return mask[idx] ? inv_keep : 0.0f;
+    if (p <= 0.0f) return 1.0f;
+    float u = (float)(mix64(seed * 0x9E3779B97F4A7C15ull + idx) >> 40) * (1.0f / 16777216.0f);
+    return (u >= p) ? inv_keep : 0.0f;
+}
+
+// x [B,T,F] (rows b0..b0+Bm) -> xt [(t*Bm+b)][F]
+__global__ void dr_time_major_kernel(const float* __restrict__ x, float* __restrict__ xt, int b0, int Bm, int T, int F) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)T * Bm * F;
+    if (i >= total) return;
+    int f = (int)(i % F); size_t r = i / F;
+    int b = (int)(r % Bm); int t = (int)(r / Bm);
+    xt[i] = x[((size_t)(b0 + b) * T + t) * F + f];
+}
+
+// gi[e][(t,b)][3H] += b_ih   (after the input-projection GEMM)
+__global__ void dr_add_bias_kernel(float* __restrict__ gi, const float* __restrict__ blob, int off_b, int pe, size_t rows_per_e, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c = (int)(i % (3 * DR_H)); size_t r = i / (3 * DR_H);
+    int e = (int)(r / rows_per_e);
+    gi[i] += blob[(size_t)e * pe + off_b + c];
+}
+
+// one forward time step for every local expert of one direction (GRU equations)
+//   gi : [e][(t,b)][3H] (x projection + b_ih)      gh: [e][b][3H] (h_{t-1} W_hh^T, no bias)
+//   saves rzn[e][(t,b)][3H] = (r,z,n), q[e][(t,b)][H] = W_hn h + b_hn, hs[e][(t,b)][H] = h_t
+__global__ void dr_gate_fwd_kernel(const float* __restrict__ gi, const float* __restrict__ gh, const float* __restrict__ hprev,
+                                   const float* __restrict__ blob, int off_bhh, int pe,
+                                   float* __restrict__ rzn, float* __restrict__ q, float* __restrict__ hs,
+                                   int t, int Bm, int T, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int j = (int)(i % DR_H); size_t r = i / DR_H;
+    int b = (int)(r % Bm); int e = (int)(r / Bm);
+    size_t row = ((size_t)e * T + t) * Bm + b;
+    const float* g = gi + row * 3 * DR_H;
+    const float* h3 = gh + ((size_t)e * Bm + b) * 3 * DR_H;
+    const float* bh = blob + (size_t)e * pe + off_bhh;
+    float rr = 1.0f / (1.0f + expf(-(g[j] + h3[j] + bh[j])));
+    float zz = 1.0f / (1.0f + expf(-(g[DR_H + j] + h3[DR_H + j] + bh[DR_H + j])));
+    float qq = h3[2 * DR_H + j] + bh[2 * DR_H + j];
+    float nn = tanhf(g[2 * DR_H + j] + rr * qq);
+    float hp = hprev ? hprev[((size_t)e * T * Bm + b) * DR_H + j] : 0.0f;   // hprev points at hs[e=0][(t_prev,0)]
+    float hn = __fadd_rn(__fmul_rn(__fsub_rn(hp, nn), zz), nn);
+    rzn[row * 3 * DR_H + j] = rr; rzn[row * 3 * DR_H + DR_H + j] = zz; rzn[row * 3 * DR_H + 2 * DR_H + j] = nn;
+    q[row * DR_H + j] = qq;
+    hs[row * DR_H + j] = hn;
+}
+
+// S[(t,b)][2H] = sum over local experts of dropout(h)   (deterministic: no atomics)
+__global__ void dr_sum_experts_kernel(const float* __restrict__ hs0, const float* __restrict__ hs1, const uint8_t* __restrict__ mask, uint64_t seed, float p,
+                                      float* __restrict__ S, int M_loc, int e_lo, int B, int b0, int Bm, int T, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int k = (int)(i % DR_2H); size_t r = i / DR_2H;
+    int b = (int)(r % Bm); int t = (int)(r / Bm);
+    int d = k / DR_H, j = k % DR_H;
+    float inv_keep = 1.0f / (1.0f - p);
+    float acc = 0.0f;
+    for (int e = 0; e < M_loc; ++e) {
+        float h = (d ? hs1 : hs0)[(((size_t)e * T + t) * Bm + b) * DR_H + j];
+        size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
+        acc += h * keep_scale(mask, seed, midx, p, inv_keep);
+    }
+    S[i] = acc;
+}
+
+// out[b,t,e,q] = sum_k Ct[e][d][q][j] r~_e + sum_k Abar[e][q][k] S + hb ; one warp per (t,b,e)
+__global__ void dr_head_fwd_kernel(const float* __restrict__ hs0, const float* __restrict__ hs1, const float* __restrict__ S, const uint8_t* __restrict__ mask,
+                                   uint64_t seed, float p, const float* __restrict__ ct, const float* __restrict__ abar,
+                                   const float* __restrict__ hb, float* __restrict__ out,
+                                   int M_loc, int e_lo, int B, int b0, int Bm, int T) {
+    size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    size_t total = (size_t)T * Bm * M_loc;
+    if (w >= total) return;
+    int e = (int)(w % M_loc); size_t r = w / M_loc;
+    int b = (int)(r % Bm); int t = (int)(r / Bm);
+    float inv_keep = 1.0f / (1.0f - p);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int k = lane; k < DR_2H; k += 32) {
+        int d = k / DR_H, j = k % DR_H;
+        float h = (d ? hs1 : hs0)[(((size_t)e * T + t) * Bm + b) * DR_H + j];
+        size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
+        float rt = h * keep_scale(mask, seed, midx, p, inv_keep);
+        float s = S[((size_t)t * Bm + b) * DR_2H + k];
+        const float* c = ct + ((size_t)(e * 2 + d) * DR_Q) * DR_H + j;
+        const float* a = abar + ((size_t)e * DR_Q) * DR_2H + k;
+        a0 += c[0] * rt + a[0] * s;
+        a1 += c[DR_H] * rt + a[DR_2H] * s;
+        a2 += c[2 * DR_H] * rt + a[2 * DR_2H] * s;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        float* o = out + (((size_t)(b0 + b) * T + t) * M_loc + e) * DR_Q;
+        o[0] = a0 + hb[e * DR_Q]; o[1] = a1 + hb[e * DR_Q + 1]; o[2] = a2 + hb[e * DR_Q + 2];
+    }
+}
+
+// dL/dout (qrnn.py:58-67 through torch.max's tie rule) and the loss partial sum
+__global__ void dr_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ y, float* __restrict__ dy,
+                                    size_t n_rm, float q0, float q1, float q2, float inv_n, double* acc) {
+    float local = 0.0f;
+    const float qs[3] = {q0, q1, q2};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rm; i += (size_t)gridDim.x * blockDim.x) {
+        float yy = y[i];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float e = yy - out[i * DR_Q + k];
+            local += fmaxf((qs[k] - 1.0f) * e, qs[k] * e);
+            float g = (e < 0.0f) ? (1.0f - qs[k]) : (e > 0.0f) ? -qs[k] : (0.5f - qs[k]);
+            dy[i * DR_Q + k] = g * inv_n;
+        }
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = (double)local;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) { if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s]; __syncthreads(); }
+    if (threadIdx.x == 0) atomicAdd(acc, red[0]);
+}
+
+// Gbar[(t,b)][k] = sum_{e,q} Abar[e][q][k] dy[b,t,e,q]
+__global__ void dr_gbar_kernel(const float* __restrict__ dy, const float* __restrict__ abar, float* __restrict__ gbar,
+                               int M_loc, int b0, int Bm, int T, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int k = (int)(i % DR_2H); size_t r = i / DR_2H;
+    int b = (int)(r % Bm); int t = (int)(r / Bm);
+    const float* d = dy + ((size_t)(b0 + b) * T + t) * M_loc * DR_Q;
+    float acc = 0.0f;
+    for (int eq = 0; eq < M_loc * DR_Q; ++eq) acc = fmaf(abar[(size_t)eq * DR_2H + k], d[eq], acc);
+    gbar[i] = acc;
+}
+
+// d(h_t) that enters the GRU backward: dropout adjoint of (Ct^T dy + Gbar)     dhout[d][e][(t,b)][H]
+__global__ void dr_dhout_kernel(const float* __restrict__ dy, const float* __restrict__ gbar, const float* __restrict__ ct,
+                                const uint8_t* __restrict__ mask, uint64_t seed, float p, float* __restrict__ dhout,
+                                int M_loc, int e_lo, int B, int b0, int Bm, int T, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int j = (int)(i % DR_H); size_t r = i / DR_H;
+    int b = (int)(r % Bm); r /= Bm;
+    int t = (int)(r % T); r /= T;
+    int e = (int)(r % M_loc); int d = (int)(r / M_loc);
+    int k = d * DR_H + j;
+    const float* dd = dy + (((size_t)(b0 + b) * T + t) * M_loc + e) * DR_Q;
+    const float* c = ct + ((size_t)(e * 2 + d) * DR_Q) * DR_H + j;
+    float v = c[0] * dd[0] + c[DR_H] * dd[1] + c[2 * DR_H] * dd[2] + gbar[((size_t)t * Bm + b) * DR_2H + k];
+    size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
+    dhout[i] = v * keep_scale(mask, seed, midx, p, 1.0f / (1.0f - p));
+}
+
+// head weight gradients: U[e][q][k] = sum_{t,b} dy r~ ; V = sum dy S ; db = sum dy.   grid (M_loc, chunks), 256 threads = k
+__global__ void dr_head_grad_kernel(const float* __restrict__ hs0, const float* __restrict__ hs1, const float* __restrict__ S, const float* __restrict__ dy,
+                                    const uint8_t* __restrict__ mask, uint64_t seed, float p, float* __restrict__ gblob,
+                                    int off_hw, int off_hb, int pe, float inv_m1,
+                                    int M_loc, int e_lo, int B, int b0, int Bm, int T, int rows_per_chunk) {
+    int e = blockIdx.x, k = threadIdx.x;
+    int d = k / DR_H, j = k % DR_H;
+    size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+    size_t rows = (size_t)T * Bm;
+    if (r1 > rows) r1 = rows;
+    float inv_keep = 1.0f / (1.0f - p);
+    float u[3] = {0, 0, 0}, v[3] = {0, 0, 0}, sb[3] = {0, 0, 0};
+    for (size_t r = r0; r < r1; ++r) {
+        int t = (int)(r / Bm), b = (int)(r % Bm);
+        float h = (d ? hs1 : hs0)[(((size_t)e * T + t) * Bm + b) * DR_H + j];
+        size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
+        float rt = h * keep_scale(mask, seed, midx, p, inv_keep);
+        float s = S[r * DR_2H + k];
+        const float* dd = dy + (((size_t)(b0 + b) * T + t) * M_loc + e) * DR_Q;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { u[q] = fmaf(dd[q], rt, u[q]); v[q] = fmaf(dd[q], s, v[q]); if (k == 0) sb[q] += dd[q]; }
+    }
+    float* hw = gblob + (size_t)e * pe + off_hw;      // [Q][4H]: cols 0..2H-1 = A (mean part), 2H.. = C (own part)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        atomicAdd(hw + (size_t)q * 4 * DR_H + DR_2H + k, u[q]);
+        atomicAdd(hw + (size_t)q * 4 * DR_H + k, (v[q] - u[q]) * inv_m1);
+        if (k == 0) atomicAdd(gblob + (size_t)e * pe + off_hb + q, sb[q]);
+    }
+}
+
+// one backward time step for one direction: gate adjoints in place (rzn -> dgh, gi -> dgi), dh carry *= z
+__global__ void dr_gate_bwd_kernel(float* __restrict__ rzn, float* __restrict__ gi, const float* __restrict__ q,
+                                   const float* __restrict__ hprev, const float* __restrict__ dhout, float* __restrict__ dhc,
+                                   int t, int Bm, int T, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int j = (int)(i % DR_H); size_t r = i / DR_H;
+    int b = (int)(r % Bm); int e = (int)(r / Bm);
+    size_t row = ((size_t)e * T + t) * Bm + b;
+    float rr = rzn[row * 3 * DR_H + j], zz = rzn[row * 3 * DR_H + DR_H + j], nn = rzn[row * 3 * DR_H + 2 * DR_H + j];
+    float qq = q[row * DR_H + j];
+    float hp = hprev ? hprev[((size_t)e * T * Bm + b) * DR_H + j] : 0.0f;
+    float dh = dhc[((size_t)e * Bm + b) * DR_H + j] + dhout[row * DR_H + j];
+    float dn = dh * (1.0f - zz);
+    float dz = dh * (hp - nn);
+    float dan = dn * (1.0f - nn * nn);
+    float dr = dan * qq;
+    float dq = dan * rr;
+    float daz = dz * zz * (1.0f - zz);
+    float dar = dr * rr * (1.0f - rr);
+    gi[row * 3 * DR_H + j] = dar; gi[row * 3 * DR_H + DR_H + j] = daz; gi[row * 3 * DR_H + 2 * DR_H + j] = dan;     // dgi
+    rzn[row * 3 * DR_H + j] = dar; rzn[row * 3 * DR_H + DR_H + j] = daz; rzn[row * 3 * DR_H + 2 * DR_H + j] = dq;  // dgh
+    dhc[((size_t)e * Bm + b) * DR_H + j] = dh * zz;        // + dgh W_hh is added by the GEMM that follows
+}
+
+// column sums: dst[e*pe + off + c] += sum over rows of src[e][row][c]   grid (M_loc, chunks), 3H threads
+__global__ void dr_colsum_kernel(const float* __restrict__ src, float* __restrict__ gblob, int off, int pe,
+                                 size_t rows, int rows_per_chunk) {
+    int e = blockIdx.x, c = threadIdx.x;
+    size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+    if (r1 > rows) r1 = rows;
+    float acc = 0.0f;
+    for (size_t r = r0; r < r1; ++r) acc += src[((size_t)e * rows + r) * 3 * DR_H + c];
+    atomicAdd(gblob + (size_t)e * pe + off + c, acc);
+}
+
+// from P[e][3H][F] = sum dgi (x) x :  dW_ih += P * mask ;  dmask[e][f] += sum_i W_ih[i][f] P[i][f]
+__global__ void dr_wih_grad_kernel(const float* __restrict__ P, const float* __restrict__ blob, const float* __restrict__ mask,
+                                   float* __restrict__ gblob, float* __restrict__ dmask, int off_wih, int pe, int F) {
+    int e = blockIdx.x;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float mk = mask[(size_t)e * F + f], acc = 0.0f;
+        for (int i = 0; i < 3 * DR_H; ++i) {
+            float pv = P[((size_t)e * 3 * DR_H + i) * F + f];
+            gblob[(size_t)e * pe + off_wih + (size_t)i * F + f] += pv * mk;
+            acc = fmaf(blob[(size_t)e * pe + off_wih + (size_t)i * F + f], pv, acc);
+        }
+        dmask[(size_t)e * F + f] += acc;
+    }
+}
+
+// softmax / Linear / ReLU / Linear adjoints of the mask MLP (qrnn.py:34); one block per expert, H threads
+__global__ void dr_mask_bwd_kernel(const float* __restrict__ blob, DrBlobOffsets off, int F, const float* __restrict__ mask,
+                                   const float* __restrict__ dmask, float* __restrict__ gblob) {
+    extern __shared__ float sm[];            // dlogit[F]
+    int e = blockIdx.x, tid = threadIdx.x;
+    const float* ex = blob + (size_t)e * off.per_expert;
+    float* gx = gblob + (size_t)e * off.per_expert;
+    float dot = 0.0f;
+    for (int f = 0; f < F; ++f) dot += mask[(size_t)e * F + f] * dmask[(size_t)e * F + f];
+    for (int f = tid; f < F; f += blockDim.x) sm[f] = mask[(size_t)e * F + f] * (dmask[(size_t)e * F + f] - dot);
+    __syncthreads();
+    float pre = ex[off.mask_w1 + tid] + ex[off.mask_b1 + tid];
+    float hid = fmaxf(pre, 0.0f);
+    float dhid = 0.0f;
+    for (int f = 0; f < F; ++f) {
+        gx[off.mask_w2 + (size_t)f * DR_H + tid] += sm[f] * hid;
+        dhid = fmaf(ex[off.mask_w2 + (size_t)f * DR_H + tid], sm[f], dhid);
+    }
+    if (pre <= 0.0f) dhid = 0.0f;
+    gx[off.mask_w1 + tid] += dhid;
+    gx[off.mask_b1 + tid] += dhid;
+    for (int f = tid; f < F; f += blockDim.x) gx[off.mask_b2 + f] += sm[f];
+}
+
+// torch.optim.Adam defaults, in torch's operation order (estimate.py:61,74)
+__global__ void dr_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                               size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2, float eps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float gi = g[i];
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
+    w[i] = w[i] - lr_over_bc1 * (mi / denom);
+}
+
+__global__ void dr_finish_loss_kernel(const double* acc, double inv_n, float* loss) { *loss = (float)(*acc * inv_n); }
+
+inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+int gemm(dr_model* m, const Gemm& g, int batch) {
+    if (g.M <= 0 || g.N <= 0 || batch <= 0) return DR_OK;
+    dim3 grid((g.N + GT - 1) / GT, (g.M + GT - 1) / GT, batch);
+    dr_bgemm_kernel<<<grid, 256, 0, m->stream>>>(g);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct dr_train_ws {
+    float *xt, *gi, *rzn, *q, *hs, *dhout, *gh, *dhc, *S, *gbar, *dy, *P, *dmask;
+    size_t cap_rows; int cap_B; int cap_T;
+};
+
+static int ws_alloc(dr_model* m, float** p, size_t n) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    cudaError_t e = cudaMalloc((void**)p, (n ? n : 4) * sizeof(float));
+    if (e != cudaSuccess) return dr_cuda_fail(m, e, "cudaMalloc(training workspace)");
+    return DR_OK;
+}
+
+int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
+                       float lr, float* loss_dev, float* out_dev) {
+    const int F = m->cfg.F, Ml = m->M_loc, M = m->cfg.M, pe = m->off.per_expert;
+    const float p = m->cfg.dropout_p;
+    if (p >= 1.0f) return dr_fail(m, DR_EINVAL, "dropout_p must be < 1");
+    if (m->cfg.world != 1) return dr_fail(m, DR_EUNSUPPORTED, "dr_train_step: expert-sharded training is not built yet (world must be 1)");
+
+    // micro-batch size from a memory budget (4.5 KB per expert-window-step-direction, see header)
+    size_t per_window = (size_t)2 * Ml * T * (3 * DR_H * 2 + DR_H * 3) * sizeof(float);
+    size_t budget = (size_t)24 << 30;
+    int Bm = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, budget / per_window));
+    if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) Bm = std::min(B, v); }   // test hook
+    dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
+    if (!ws) { ws = new dr_train_ws(); memset(ws, 0, sizeof(*ws)); m->train_ws = ws; }
+    size_t rows = (size_t)T * Bm, E2 = (size_t)2 * Ml;
+    if (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T) {
+        int rc;
+        if ((rc = ws_alloc(m, &ws->xt, rows * F)) || (rc = ws_alloc(m, &ws->gi, E2 * rows * 3 * DR_H)) ||
+            (rc = ws_alloc(m, &ws->rzn, E2 * rows * 3 * DR_H)) || (rc = ws_alloc(m, &ws->q, E2 * rows * DR_H)) ||
+            (rc = ws_alloc(m, &ws->hs, E2 * rows * DR_H)) || (rc = ws_alloc(m, &ws->dhout, E2 * rows * DR_H)) ||
+            (rc = ws_alloc(m, &ws->gh, (size_t)Ml * Bm * 3 * DR_H)) || (rc = ws_alloc(m, &ws->dhc, (size_t)Ml * Bm * DR_H)) ||
+            (rc = ws_alloc(m, &ws->S, rows * DR_2H)) || (rc = ws_alloc(m, &ws->gbar, rows * DR_2H)) ||
+            (rc = ws_alloc(m, &ws->dy, (size_t)B * T * Ml * DR_Q)) || (rc = ws_alloc(m, &ws->P, (size_t)Ml * 3 * DR_H * F)) ||
+            (rc = ws_alloc(m, &ws->dmask, (size_t)Ml * F)))
+            return rc;
+        ws->cap_rows = rows; ws->cap_B = B; ws->cap_T = T;
+    }
+    size_t nblob = (size_t)Ml * pe;
+    if (!m->d_grad) {
+        DR_CUDA(m, cudaMalloc((void**)&m->d_grad, nblob * sizeof(float)));
+        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_m, nblob * sizeof(float)));
+        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_v, nblob * sizeof(float)));
+        DR_CUDA(m, cudaMemsetAsync(m->d_adam_m, 0, nblob * sizeof(float), m->stream));
+        DR_CUDA(m, cudaMemsetAsync(m->d_adam_v, 0, nblob * sizeof(float), m->stream));
+        m->adam_step = 0;
+    }
+    DR_CUDA(m, cudaMemsetAsync(m->d_grad, 0, nblob * sizeof(float), m->stream));
+    DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
+    double* acc = reinterpret_cast<double*>(m->d_loss);
+    DR_CUDA(m, cudaMemsetAsync(acc, 0, sizeof(double), m->stream));
+    cudaStream_t st = m->stream;
+    const float inv_n = 1.0f / ((float)M * (float)B * (float)T);
+    const size_t ed_stride = (size_t)Ml * rows;        // activations are [dir][e][(t,b)][...]
+
+    // ---------------- pass 1: forward over all micro-batches (out needs every window before the loss) ------------
+    // With more than one micro-batch the activations of earlier micro-batches are recomputed in pass 2.
+    const int n_mb = (B + Bm - 1) / Bm;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int mb = 0; mb < n_mb; ++mb) {
+            const int b0 = mb * Bm, bm = std::min(Bm, B - b0);
+            const size_t r = (size_t)T * bm;
+            const bool need_fwd = (pass == 0) || (n_mb > 1);
+            if (need_fwd) {
+                dr_time_major_kernel<<<nblk(r * F), 256, 0, st>>>(x, ws->xt, b0, bm, T, F);
+                for (int d = 0; d < 2; ++d) {
+                    float* gi = ws->gi + d * ed_stride * 3 * DR_H;
+                    float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
+                    float* q = ws->q + d * ed_stride * DR_H;
+                    float* hs = ws->hs + d * ed_stride * DR_H;
+                    // gi = (x*mask) W_ih^T + b_ih, all steps at once: the mask-folded rows live in d_wf? no — use W_ih and xm explicitly:
+                    // A(m=(t,b), k=f) = xt*mask is formed on the fly by scaling B instead: B(k=f, n=i) = W_ih[i][f]*mask[f] = d_wihm
+                    Gemm g{ws->xt, m->d_wihm + (size_t)d * Ml * 3 * DR_H * F, gi, (int)r, 3 * DR_H, F,
+                           F, 1, 1, F, 3 * DR_H, 1, 0, (long)3 * DR_H * F, (long)T * bm * 3 * DR_H, 0.0f};
+                    int rc = gemm(m, g, Ml);
+                    if (rc) return rc;
+                    size_t tot = (size_t)Ml * r * 3 * DR_H;
+                    dr_add_bias_kernel<<<nblk(tot), 256, 0, st>>>(gi, m->d_blob, m->off.b_ih[d], pe, r, tot);
+                    for (int s = 0; s < T; ++s) {
+                        const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
+                        const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
+                        if (s == 0) {
+                            DR_CUDA(m, cudaMemsetAsync(ws->gh, 0, (size_t)Ml * bm * 3 * DR_H * sizeof(float), st));
+                        } else {
+                            Gemm gh{hprev, m->d_blob + m->off.w_hh[d], ws->gh, bm, 3 * DR_H, DR_H,
+                                    DR_H, 1, 1, DR_H, 3 * DR_H, 1, (long)T * bm * DR_H, (long)pe, (long)bm * 3 * DR_H, 0.0f};
+                            rc = gemm(m, gh, Ml);
+                            if (rc) return rc;
+                        }
+                        size_t tg = (size_t)Ml * bm * DR_H;
+                        dr_gate_fwd_kernel<<<nblk(tg), 256, 0, st>>>(gi, ws->gh, hprev, m->d_blob, m->off.b_hh[d], pe,
+                                                                      rzn, q, hs, t, bm, T, tg);
+                    }
+                }
+                size_t ts = r * DR_2H;
+                dr_sum_experts_kernel<<<nblk(ts), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, mask, seed, p, ws->S, Ml, m->e_lo, B, b0, bm, T, ts);
+                if (pass == 0) {
+                    size_t tw = r * Ml * 32;
+                    dr_head_fwd_kernel<<<nblk(tw), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, mask, seed, p, m->d_ct, m->d_abar, m->d_hb,
+                                                                  out_dev, Ml, m->e_lo, B, b0, bm, T);
+                }
+                DR_CUDA(m, cudaGetLastError());
+                m->launches += 4 + 2 * (2 + 2 * T);
+            }
+            if (pass == 0) {
+                if (mb == n_mb - 1) {
+                    size_t n_rm = (size_t)B * T * M;
+                    unsigned blocks = std::min<unsigned>(nblk(n_rm), 148u * 8u);
+                    dr_loss_grad_kernel<<<blocks, 256, 0, st>>>(out_dev, y, ws->dy, n_rm, m->cfg.quantiles[0], m->cfg.quantiles[1],
+                                                                 m->cfg.quantiles[2], inv_n, acc);
+                    dr_finish_loss_kernel<<<1, 1, 0, st>>>(acc, (double)inv_n, loss_dev);
+                    DR_CUDA(m, cudaGetLastError());
+                    m->launches += 2;
+                }
+                continue;
+            }
+            // ---------------- pass 2: backward of this micro-batch ----------------
+            size_t ts = r * DR_2H;
+            dr_gbar_kernel<<<nblk(ts), 256, 0, st>>>(ws->dy, m->d_abar, ws->gbar, Ml, b0, bm, T, ts);
+            size_t td = (size_t)2 * Ml * r * DR_H;
+            // dhout is laid out [d][e][(t,b)][H] with the SAME (t,b) row stride as hs of this micro-batch
+            dr_dhout_kernel<<<nblk(td), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, mask, seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
+            {
+                int chunk = 2048;
+                dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
+                dr_head_grad_kernel<<<grid, DR_2H, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, ws->dy, mask, seed, p, m->d_grad, m->off.head_w,
+                                                             m->off.head_b, pe, 1.0f / (float)(M - 1), Ml, m->e_lo, B, b0, bm, T, chunk);
+            }
+            DR_CUDA(m, cudaGetLastError());
+            m->launches += 3;
+            for (int d = 0; d < 2; ++d) {
+                float* gi = ws->gi + d * ed_stride * 3 * DR_H;
+                float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
+                float* q = ws->q + d * ed_stride * DR_H;
+                float* hs = ws->hs + d * ed_stride * DR_H;
+                float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
+                DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
+                for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
+                    const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
+                    const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
+                    size_t tg = (size_t)Ml * bm * DR_H;
+                    dr_gate_bwd_kernel<<<nblk(tg), 256, 0, st>>>(rzn, gi, q, hprev, dho, ws->dhc, t, bm, T, tg);
+                    if (s > 0) {   // dh_{prev} = dh*z + dgh W_hh
+                        Gemm gd{rzn + (size_t)t * bm * 3 * DR_H, m->d_blob + m->off.w_hh[d], ws->dhc, bm, DR_H, 3 * DR_H,
+                                3 * DR_H, 1, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)pe, (long)bm * DR_H, 1.0f};
+                        int rc = gemm(m, gd, Ml);
+                        if (rc) return rc;
+                    }
+                }
+                // weight gradients over all (t,b) of the micro-batch
+                //  dW_hh += dgh^T h_prev : skip the step whose h_prev is the zero initial state
+                {
+                    const size_t skip = (size_t)bm;              // one time step of rows
+                    const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
+                    const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
+                    if (T > 1) {
+                        Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
+                                1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
+                        int rc = gemm(m, gw, Ml);
+                        if (rc) return rc;
+                    }
+                    Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
+                            (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
+                    int rc = gemm(m, gp, Ml);
+                    if (rc) return rc;
+                    dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
+                    int chunk = 1024;
+                    dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
+                    dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);
+                    dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(gi, m->d_grad, m->off.b_ih[d], pe, r, chunk);
+                    DR_CUDA(m, cudaGetLastError());
+                    m->launches += 3 + 2 * T;
+                }
+            }
+        }
+    }
+    dr_mask_bwd_kernel<<<Ml, DR_H, F * sizeof(float), st>>>(m->d_blob, m->off, F, m->d_mask, ws->dmask, m->d_grad);
+    // ---------------- Adam ----------------
+    m->adam_step += 1;
+    const double b1 = 0.9, b2 = 0.999;
+    double bc1 = 1.0 - pow(b1, (double)m->adam_step), bc2 = 1.0 - pow(b2, (double)m->adam_step);
+    dr_adam_kernel<<<nblk(nblob), 256, 0, st>>>(m->d_blob, m->d_grad, m->d_adam_m, m->d_adam_v, nblob,
+                                                (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2, 1e-8f);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 2;
+    int rc = dr_launch_prep(m);                 // the inference images follow the new weights
+    if (rc) return rc;
+    return dr_tc_prep_weights(m);
+}
+
+extern "C" {
+
+int dr_train_step_dev(dr_model* m, const float* x_dev, const float* y_dev, int32_t B, int32_t T,
+                      const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev, float* out_dev) {
+    if (!m) return DR_EINVAL;
+    if (!x_dev || !y_dev || !loss_dev || !out_dev || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "dr_train_step_dev: bad argument");
+    if (!m->loaded) return dr_fail(m, DR_ESTATE, "train step before dr_load_weights");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    return dr_train_step_impl(m, x_dev, y_dev, B, T, dropout_mask_dev, seed, lr, loss_dev, out_dev);
+}
+
+int dr_train_step(dr_model* m, const float* x, const float* y, int32_t B, int32_t T,
+                  const uint8_t* dropout_mask, uint64_t seed, float lr, float* loss_out) {
+    if (!m) return DR_EINVAL;
+    if (!x || !y || !loss_out || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "dr_train_step: bad argument");
+    if (!m->loaded) return dr_fail(m, DR_ESTATE, "train step before dr_load_weights");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    size_t nx = (size_t)B * T * m->cfg.F, ny = (size_t)B * T * m->cfg.M, no = ny * DR_Q, nm = (size_t)m->cfg.M * B * T * DR_2H;
+    int rc;
+    if ((rc = dr_reserve(m, (void**)&m->d_xin, &m->xin_cap, nx * sizeof(float)))) return rc;
+    if ((rc = dr_reserve(m, (void**)&m->d_y, &m->y_cap, ny * sizeof(float)))) return rc;
+    if ((rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float)))) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(m->d_xin, x, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    DR_CUDA(m, cudaMemcpyAsync(m->d_y, y, ny * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    uint8_t* dmask = nullptr;
+    if (dropout_mask) {
+        if ((rc = dr_reserve(m, (void**)&m->d_dropmask, &m->dropmask_cap, nm))) return rc;
+        dmask = reinterpret_cast<uint8_t*>(m->d_dropmask);
+        DR_CUDA(m, cudaMemcpyAsync(dmask, dropout_mask, nm, cudaMemcpyHostToDevice, m->stream));
+    }
+    rc = dr_train_step_impl(m, m->d_xin, m->d_y, B, T, dmask, seed, lr, m->d_loss + 4, m->d_out);
+    if (rc) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(loss_out, m->d_loss + 4, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+int dr_get_grads(dr_model* m, float* host_blob, size_t n) {
+    if (!m) return DR_EINVAL;
+    size_t pe = (size_t)m->off.per_expert;
+    if (!host_blob || n != pe * m->cfg.M) return dr_fail(m, DR_EINVAL, "dr_get_grads: wrong blob size");
+    if (!m->d_grad) return dr_fail(m, DR_ESTATE, "dr_get_grads before any train step");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    DR_CUDA(m, cudaMemcpyAsync(host_blob + (size_t)m->e_lo * pe, m->d_grad, (size_t)m->M_loc * pe * sizeof(float),
+                               cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+}  // extern "C"
+
+void dr_train_free(dr_model* m) {
+    dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
+    if (!ws) return;
+    float* ptrs[] = {ws->xt, ws->gi, ws->rzn, ws->q, ws->hs, ws->dhout, ws->gh, ws->dhc, ws->S, ws->gbar, ws->dy, ws->P, ws->dmask};
+    for (float* p : ptrs) if (p) cudaFree(p);
+    delete ws;
+    m->train_ws = nullptr;
+}

@@ -187,6 +187,35 @@ class QuantileRNN:
                                s_elems=lib.dr_s_elems(B, T), local_fn=local_fn, heads_fn=heads_fn,
                                interleave_fn=interleave_fn, group=self._pg)
 
+    # ---- training ----------------------------------------------------------------------
+    def train_step(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0):
+        """One iteration of the reference training loop (estimate.py:67-74): train-mode forward
+        (dropout on the GRU outputs), ``quantile_loss``, backward, ``Adam(lr)`` step.  Returns the
+        loss (float).  ``dropout_mask`` ([M,B,T,2H] of 0/1) replays a mask for parity tests;
+        otherwise a counter-based RNG keyed by ``seed`` draws it on the device."""
+        x = np.ascontiguousarray(inputs.detach().cpu().numpy() if _is_torch(inputs) else inputs, np.float32)
+        y = np.ascontiguousarray(labels.detach().cpu().numpy() if _is_torch(labels) else labels, np.float32)
+        if x.ndim != 3 or x.shape[2] != self.input_size or y.shape != (x.shape[0], x.shape[1], self.num_metrics):
+            raise ValueError("inputs must be [B,T,F] and labels [B,T,M]")
+        B, T, _ = x.shape
+        mptr = None
+        if dropout_mask is not None:
+            dm = np.ascontiguousarray(dropout_mask, np.uint8)
+            if dm.shape != (self.num_metrics, B, T, 2 * layout.H):
+                raise ValueError("dropout_mask must be [M,B,T,2H]")
+            mptr = dm.ctypes.data_as(C.c_void_p)
+        loss = C.c_float()
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_train_step(self._h, x.ctypes.data_as(fp), y.ctypes.data_as(fp), B, T, mptr,
+                                                    C.c_uint64(int(seed)), C.c_float(lr), C.byref(loss)))
+        return float(loss.value)
+
+    def grads(self):
+        """Gradients of the last ``train_step`` as a blob in ``state_dict`` order."""
+        out = np.zeros(layout.blob_size(self.num_metrics, self.input_size), np.float32)
+        _lib.check(self._h, self._lib.dr_get_grads(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), out.size))
+        return out
+
     # ---- loss ------------------------------------------------------------------------
     def quantile_loss(self, outputs, labels):
         if _is_torch(outputs) and outputs.is_cuda:

@@ -113,6 +113,20 @@ int  dr_quantile_loss    (dr_model* m, const float* out_host, const float* y_hos
 int  dr_quantile_loss_dev(dr_model* m, const float* out_dev, const float* y_dev,
                           int32_t B, int32_t T, float* loss_dev);
 
+/* ---- training step: replaces one iteration of estimate.py:67-74 ----
+ *   outputs = model(inputs)  [train mode: dropout(p) on the GRU outputs, qrnn.py:43]
+ *   loss = model.quantile_loss(outputs, labels); optimizer.zero_grad(); loss.backward(); optimizer.step()
+ * with torch.optim.Adam(lr) defaults (estimate.py:61); Adam state lives in the handle.
+ * x [B,T,F], y [B,T,M].  dropout_mask (nullable): replayed keep-mask, uint8 [M,B,T,2H] in the
+ * reference's rnn_out element order (parity tests); NULL -> counter-based RNG keyed by `seed`.
+ * Round 1: world must be 1.  dr_get_grads returns the gradients of the last step (blob order). */
+int  dr_train_step    (dr_model* m, const float* x_host, const float* y_host, int32_t B, int32_t T,
+                       const uint8_t* dropout_mask_host, uint64_t seed, float lr, float* loss_host);
+int  dr_train_step_dev(dr_model* m, const float* x_dev, const float* y_dev, int32_t B, int32_t T,
+                       const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev,
+                       float* out_dev /* [B,T,M,Q] train-mode forecasts */);
+int  dr_get_grads     (dr_model* m, float* host_blob, size_t n_floats);
+
 /* ---- test/diagnostic access to prepared tensors (not on the hot path) ----
  * what: "mask" [M_loc,F] (qrnn.py:34), "S" (dr_s_elems floats, layout above) of the last
  * dr_forward/dr_forward_dev, "ct", "bias4". Returns DR_EINVAL for unknown names. */

@@ -163,3 +163,115 @@ def normalization_minmax(Mx, split):
 def sliding_window(ts, window):
     """utils.py:4-5 — stride-1 windows; NOTE drops the final window (range(len−W))."""
     return np.asarray([ts[i:i + window] for i in range(len(ts) - window)])
+
+
+# ---------------------------------------------------------------------------------------------
+# Training step: what ``loss.backward(); optimizer.step()`` computes (estimate.py:70-74).
+# The reference has no backward code — it is torch autograd over qrnn.py:28-67 — so this is a
+# restatement of those adjoints (SURVEY §8a "Backward"), pinned by tests/golden/g5_train_step.npz.
+# ---------------------------------------------------------------------------------------------
+
+def _gru_direction_backward(keep, d_out, w_ih, w_hh, reverse, dtype):
+    """Adjoint of :func:`gru_direction`.  d_out [T,B,H] is dL/d(output_t).
+    Returns dW_ih, dW_hh, db_ih, db_hh, dxm [T,B,F]."""
+    T, B, _ = d_out.shape
+    F = w_ih.shape[1]
+    w_ih = w_ih.astype(dtype); w_hh = w_hh.astype(dtype)
+    dW_ih = np.zeros_like(w_ih); dW_hh = np.zeros_like(w_hh)
+    db_ih = np.zeros(3 * H, dtype); db_hh = np.zeros(3 * H, dtype)
+    dxm = np.zeros((T, B, F), dtype)
+    dh = np.zeros((B, H), dtype)
+    xm = keep["xm"]
+    steps = range(T) if reverse else range(T - 1, -1, -1)     # opposite to the forward order
+    for t in steps:
+        r, z, n, q, hp = keep["r"][t], keep["z"][t], keep["n"][t], keep["q"][t], keep["hprev"][t]
+        dh = dh + d_out[t]
+        dn = dh * (1.0 - z)
+        dz = dh * (hp - n)
+        da_n = dn * (1.0 - n * n)
+        dr = da_n * q
+        dq = da_n * r
+        da_z = dz * z * (1.0 - z)
+        da_r = dr * r * (1.0 - r)
+        dgi = np.concatenate([da_r, da_z, da_n], axis=1)
+        dgh = np.concatenate([da_r, da_z, dq], axis=1)
+        dW_hh += dgh.T @ hp
+        db_hh += dgh.sum(0)
+        dW_ih += dgi.T @ xm[t]
+        db_ih += dgi.sum(0)
+        dxm[t] = dgi @ w_ih
+        dh = dh * z + dgh @ w_hh
+    return dW_ih, dW_hh, db_ih, db_hh, dxm
+
+
+def loss_and_grads(blob, x, y, M, F, dropout_masks=None, dropout_p=0.5, quantiles=QUANTILES, dtype=np.float32):
+    """One forward+backward of the reference training step.  Returns (loss, out, grad_blob)."""
+    from deeprest_b200.layout import expert_offsets, params_per_expert
+    blob = np.asarray(blob)
+    experts = unpack_blob(blob, M, F)
+    keep = {}
+    out = forward(blob, x, M, F, dtype, dropout_masks, dropout_p, keep)
+    loss = quantile_loss(out, y, quantiles, dtype)
+    dout = quantile_loss_grad(out, y, quantiles, dtype)                       # [B,T,M,Q]
+    rt = keep["rnn_outs"]                                                     # r~_j (after dropout)  [B,T,2H]
+    pe = params_per_expert(F)
+    offs = expert_offsets(F)
+    gblob = np.zeros(M * pe, dtype)
+
+    def put(e, name, g):
+        o, shape = offs[name]
+        gblob[e * pe + o: e * pe + o + g.size] = g.astype(dtype).reshape(-1)
+
+    d_rt = [np.zeros_like(rt[0]) for _ in range(M)]
+    Bsz, T = out.shape[:2]
+    for i, ex in enumerate(experts):                                          # head adjoint, qrnn.py:46-54
+        W = ex["head_w"].astype(dtype)
+        m_i = np.stack([rt[j] for j in range(M) if j != i]).mean(axis=0, dtype=dtype)
+        cat = np.concatenate([m_i, rt[i]], axis=-1).reshape(Bsz * T, 4 * H)
+        dy = dout[:, :, i, :].reshape(Bsz * T, Q)
+        put(i, "head_w", dy.T @ cat)
+        put(i, "head_b", dy.sum(0))
+        dcat = (dy @ W).reshape(Bsz, T, 4 * H)
+        d_rt[i] += dcat[..., 2 * H:]
+        share = dcat[..., :2 * H] / dtype(M - 1)
+        for j in range(M):
+            if j != i:
+                d_rt[j] += share
+    for e, ex in enumerate(experts):
+        ke = keep["experts"][e]
+        d_r = d_rt[e]
+        if dropout_masks is not None:
+            d_r = d_r * dropout_masks[e].astype(dtype) * dtype(1.0 / (1.0 - dropout_p))
+        d_r = d_r.transpose(1, 0, 2)                                          # [T,B,2H]
+        dxm_tot = 0
+        for dname, half, rev in (("f", slice(0, H), False), ("r", slice(H, 2 * H), True)):
+            kd = dict(ke["fwd" if not rev else "rev"]); kd["xm"] = ke["xm"]
+            dWi, dWh, dbi, dbh, dxm = _gru_direction_backward(
+                kd, np.ascontiguousarray(d_r[..., half]), ex["w_ih_" + dname], ex["w_hh_" + dname], rev, dtype)
+            put(e, "w_ih_" + dname, dWi); put(e, "w_hh_" + dname, dWh)
+            put(e, "b_ih_" + dname, dbi); put(e, "b_hh_" + dname, dbh)
+            dxm_tot = dxm_tot + dxm
+        # x*mask (qrnn.py:36): dmask_f = sum_{b,t} x[b,t,f] * dxm[t,b,f]; then softmax / ReLU / Linear adjoints (qrnn.py:34)
+        dmask = (x.astype(dtype).transpose(1, 0, 2) * dxm_tot).sum(axis=(0, 1))
+        mask = ke["mask"]
+        dlogit = mask * (dmask - (mask * dmask).sum())
+        w1 = ex["mask_w1"].astype(dtype)[:, 0]
+        pre = w1 + ex["mask_b1"].astype(dtype)
+        hid = np.maximum(pre, 0)
+        put(e, "mask_w2", np.outer(dlogit, hid)); put(e, "mask_b2", dlogit)
+        dhid = (ex["mask_w2"].astype(dtype).T @ dlogit) * (pre > 0)
+        put(e, "mask_w1", dhid); put(e, "mask_b1", dhid)                       # input is the constant 1
+    return loss, out, gblob
+
+
+def adam_step(w, g, m, v, step, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, dtype=np.float32):
+    """torch.optim.Adam defaults (estimate.py:61), in torch's own operation order:
+    p -= (lr / (1-b1^t)) * m / (sqrt(v)/sqrt(1-b2^t) + eps).  Returns (w, m, v)."""
+    w = np.asarray(w, dtype); g = np.asarray(g, dtype)
+    m = (dtype(beta1) * m + dtype(1 - beta1) * g).astype(dtype)
+    v = (dtype(beta2) * v + dtype(1 - beta2) * g * g).astype(dtype)
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    denom = (np.sqrt(v) / dtype(np.sqrt(bc2)) + dtype(eps)).astype(dtype)
+    w = (w - dtype(lr / bc1) * (m / denom)).astype(dtype)
+    return w, m, v

@@ -1,0 +1,86 @@
+"""Training-step parity on the GPU: gradients of every parameter family, the loss and the
+post-Adam weights against the golden minted from the reference's autograd (G5) and against the
+numpy oracle at other shapes (incl. the micro-batched path)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR
+from deeprest_b200 import QuantileRNN, layout, synth
+from oracle import qrnn_numpy as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def check_grads(got, ref, F, tag):
+    scale = np.abs(ref).max()
+    assert np.abs(got - ref).max() <= 5e-6 * scale + 1e-9, f"{tag}: max grad err {np.abs(got - ref).max():.3e} (scale {scale:.3e})"
+    pe = layout.params_per_expert(F)
+    for name, (off, shape) in layout.expert_offsets(F).items():
+        n = int(np.prod(shape))
+        for e in range(got.size // pe):
+            a, b = got[e * pe + off:e * pe + off + n], ref[e * pe + off:e * pe + off + n]
+            tol = 2e-5 * max(np.abs(b).max(), 1e-7) + 1e-9
+            assert np.abs(a - b).max() <= tol, f"{tag}: {name}[expert {e}] err {np.abs(a - b).max():.3e} vs max {np.abs(b).max():.3e}"
+
+
+def test_train_step_matches_reference_golden():
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "g5_train_step.npz")))
+    M, B, T, F = (int(g[k]) for k in ("M", "B", "T", "F"))
+    blob = synth.weights(int(g["wseed"]), M, F, float(g["wscale"]))
+    x = synth.windows(int(g["xseed"]), B, T, F, str(g["xkind"]))
+    y = synth.labels(int(g["yseed"]), B, T, M)
+    dm = (synth.uniform(int(g["mask_seed"]), M * B * T * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(M, B, T, 2 * layout.H)
+    m = QuantileRNN(F, M)
+    try:
+        m.load_blob(blob)
+        loss = m.train_step(x, y, lr=float(g["lr"]), dropout_mask=dm)
+        grads = m.grads()
+        after = m.blob()
+    finally:
+        m.close()
+    assert abs(loss - float(g["loss"])) < 2e-6
+    check_grads(grads, g["grads"], F, "vs reference autograd")
+    assert np.abs(after - g["weights_after"]).max() < 2e-6, np.abs(after - g["weights_after"]).max()
+
+
+@pytest.mark.parametrize("M,B,T,F,mb", [(3, 5, 7, 5, 0), (2, 9, 4, 16, 4), (4, 6, 12, 33, 0)])
+def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
+    if mb:
+        monkeypatch.setenv("DR_TRAIN_MICROBATCH", str(mb))        # force the multi-micro-batch path
+    blob = synth.weights(40 + M, M, F, 1.5)
+    x = synth.windows(3, B, T, F, "diurnal")
+    y = synth.labels(4, B, T, M)
+    dm = (synth.uniform(8, M * B * T * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(M, B, T, 2 * layout.H)
+    ref_loss, _, ref_g = oracle.loss_and_grads(blob, x, y, M, F, dropout_masks=dm.astype(np.float32))
+    ref_w, _, _ = oracle.adam_step(blob, ref_g, np.zeros_like(blob), np.zeros_like(blob), step=1)
+    m = QuantileRNN(F, M)
+    try:
+        m.load_blob(blob)
+        loss = m.train_step(x, y, lr=1e-3, dropout_mask=dm)
+        grads = m.grads()
+        after = m.blob()
+        # the inference images follow the updated weights
+        out_after = m.eval()(x)
+    finally:
+        m.close()
+    assert abs(loss - float(ref_loss)) < 2e-6
+    check_grads(grads, ref_g, F, "vs oracle")
+    assert np.abs(after - ref_w).max() < 2e-6
+    ref_out = oracle.forward(after, x, M, F)
+    assert np.all(np.abs(out_after - ref_out) <= 1e-6 + 1e-4 * np.abs(ref_out))
+
+
+def test_training_reduces_the_loss_with_device_rng():
+    M, B, T, F = 2, 32, 20, 16
+    blob = synth.weights(7, M, F)
+    x = synth.windows(3, B, T, F, "diurnal")
+    y = np.clip(x[:, :, :M] * 0.5 + 0.1, 0, 1).astype(np.float32)   # learnable target
+    m = QuantileRNN(F, M, dropout=0.5)
+    try:
+        m.load_blob(blob)
+        losses = [m.train_step(x, y, lr=1e-2, seed=100 + i) for i in range(30)]
+    finally:
+        m.close()
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < 0.7 * np.mean(losses[:5]), losses

@@ -86,3 +86,56 @@ def test_torch_cpu_baseline_port_matches_reference_golden():
     g = load_golden(os.path.join(GOLDEN_DIR, "g2b_small_diurnal.npz"))
     out = TorchCpuPort(g["blob_arr"], g["M"], g["F"]).forward(g["x"])
     assert np.abs(out - g["out"]).max() < 1e-7     # same torch kernels as the reference
+
+
+def _g5():
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "g5_train_step.npz")))
+    M, B, T, F = (int(g[k]) for k in ("M", "B", "T", "F"))
+    blob = synth.weights(int(g["wseed"]), M, F, float(g["wscale"]))
+    assert abs(blob.astype(np.float64).sum() - float(g["blob_sum"])) < 1e-9
+    x = synth.windows(int(g["xseed"]), B, T, F, str(g["xkind"]))
+    y = synth.labels(int(g["yseed"]), B, T, M)
+    dm = (synth.uniform(int(g["mask_seed"]), M * B * T * 2 * layout.H) >= 0.5).astype(np.float32)
+    return g, M, B, T, F, blob, x, y, dm.reshape(M, B, T, 2 * layout.H)
+
+
+def test_train_step_grads_match_reference_autograd():
+    g, M, B, T, F, blob, x, y, dm = _g5()
+    loss, out, grads = oracle.loss_and_grads(blob, x, y, M, F, dropout_masks=dm)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    assert np.abs(out - g["out"]).max() < 1e-6
+    ref = g["grads"]
+    scale = np.abs(ref).max()
+    assert np.abs(grads - ref).max() < 2e-6 * scale + 1e-9, np.abs(grads - ref).max()
+    # per-tensor: every parameter family gets a gradient of the right size
+    for name, (off, shape) in layout.expert_offsets(F).items():
+        n = int(np.prod(shape))
+        a, b = grads[off:off + n], ref[off:off + n]
+        assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-6) + 1e-9, name
+
+
+def test_adam_step_matches_reference_optimizer():
+    g, M, B, T, F, blob, x, y, dm = _g5()
+    w, m, v = oracle.adam_step(blob, g["grads"], np.zeros_like(blob), np.zeros_like(blob), step=1, lr=float(g["lr"]))
+    assert np.abs(w - g["weights_after"]).max() < 1e-7
+
+
+def test_fp64_grads_match_finite_differences():
+    M, B, T, F = 2, 2, 3, 3
+    blob = synth.weights(9, M, F, 1.5).astype(np.float64)
+    x = synth.windows(3, B, T, F).astype(np.float64)
+    y = synth.labels(4, B, T, M).astype(np.float64)
+    dm = (synth.uniform(8, M * B * T * 2 * layout.H) >= 0.5).astype(np.float64).reshape(M, B, T, 2 * layout.H)
+    _, _, g = oracle.loss_and_grads(blob, x, y, M, F, dropout_masks=dm, dtype=np.float64)
+    rng = np.random.default_rng(0)
+    offs = layout.expert_offsets(F)
+    for name in ("mask_w1", "mask_w2", "w_ih_f", "w_hh_r", "b_hh_f", "head_w", "head_b"):
+        off, shape = offs[name]
+        idx = layout.params_per_expert(F) * int(rng.integers(M)) + off + int(rng.integers(int(np.prod(shape))))
+        eps = 1e-6
+        p = blob.copy(); p[idx] += eps
+        q = blob.copy(); q[idx] -= eps
+        lp = oracle.quantile_loss(oracle.forward(p, x, M, F, np.float64, dm), y, dtype=np.float64)
+        lq = oracle.quantile_loss(oracle.forward(q, x, M, F, np.float64, dm), y, dtype=np.float64)
+        fd = (lp - lq) / (2 * eps)
+        assert abs(fd - g[idx]) < 1e-6 * max(1.0, abs(fd)), (name, fd, g[idx])
