@@ -54,7 +54,6 @@ def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
     y = synth.labels(4, B, T, M)
     dm = (synth.uniform(8, M * B * T * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(M, B, T, 2 * layout.H)
     ref_loss, _, ref_g = oracle.loss_and_grads(blob, x, y, M, F, dropout_masks=dm.astype(np.float32))
-    ref_w, _, _ = oracle.adam_step(blob, ref_g, np.zeros_like(blob), np.zeros_like(blob), step=1)
     m = QuantileRNN(F, M)
     try:
         m.load_blob(blob)
@@ -67,7 +66,10 @@ def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
         m.close()
     assert abs(loss - float(ref_loss)) < 2e-6
     check_grads(grads, ref_g, F, "vs oracle")
-    assert np.abs(after - ref_w).max() < 2e-6
+    # Adam is checked on the GPU's own gradients: at step 1 the update is lr*g/(|g|+eps), so where |g| ~ eps a
+    # 1e-9 gradient difference legitimately moves the weight by more than any fixed tolerance
+    ref_w, _, _ = oracle.adam_step(blob, grads, np.zeros_like(blob), np.zeros_like(blob), step=1)
+    assert np.abs(after - ref_w).max() <= 3e-7 * max(1.0, np.abs(ref_w).max())
     ref_out = oracle.forward(after, x, M, F)
     assert np.all(np.abs(out_after - ref_out) <= 1e-6 + 1e-4 * np.abs(ref_out))
 
