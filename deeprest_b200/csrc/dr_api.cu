@@ -80,6 +80,8 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wtc = nullptr; m->wtc_bytes = 0;
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
+    m->copy_stream = nullptr;
+    for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
     m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
@@ -117,6 +119,8 @@ void dr_destroy(dr_model* m) {
                     m->d_xT, m->d_xtc, m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    for (int i = 0; i < 5; ++i) if (m->ev_pipe[i]) cudaEventDestroy(m->ev_pipe[i]);
     if (m->ev) { for (int i = 0; i < 4 * DR_PROF_MAX; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
     delete m;
 }
@@ -280,10 +284,42 @@ int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
     if (rc != DR_OK) return rc;
     rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float));
     if (rc != DR_OK) return rc;
-    DR_CUDA(m, cudaMemcpyAsync(m->d_xin, x, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));
-    rc = dr_forward_dev(m, m->d_xin, B, T, m->d_out);
-    if (rc != DR_OK) return rc;
-    DR_CUDA(m, cudaMemcpyAsync(out, m->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    // Windows are independent, so a large batch runs as two half-batches: the H2D copy of the second half
+    // and the D2H copy of the first half's forecasts overlap the other half's kernels (copy engine on its
+    // own stream, ordered with events).  Halves are multiples of 256 windows = whole tensor-core pair tiles.
+    int nc = (B >= 512) ? 2 : 1;
+    int Bc = (nc == 2) ? ((B / 2 + 255) / 256) * 256 : B;
+    if (nc == 2 && !m->copy_stream) {
+        DR_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; ++i) DR_CUDA(m, cudaEventCreateWithFlags(&m->ev_pipe[i], cudaEventDisableTiming));
+    }
+    if (nc == 1) {
+        DR_CUDA(m, cudaMemcpyAsync(m->d_xin, x, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+        rc = dr_forward_dev(m, m->d_xin, B, T, m->d_out);
+        if (rc != DR_OK) return rc;
+        DR_CUDA(m, cudaMemcpyAsync(out, m->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+        DR_CUDA(m, cudaStreamSynchronize(m->stream));
+        return DR_OK;
+    }
+    const size_t xrow = (size_t)T * m->cfg.F, orow = (size_t)T * m->cfg.M * DR_Q;
+    // the copy stream must not start before earlier work on the compute stream that may still use the staging buffers
+    DR_CUDA(m, cudaEventRecord(m->ev_pipe[4], m->stream));
+    DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[4], 0));
+    for (int c = 0; c < nc; ++c) {
+        int b0 = c * Bc, bn = (c == nc - 1) ? B - b0 : Bc;
+        DR_CUDA(m, cudaMemcpyAsync(m->d_xin + b0 * xrow, x + b0 * xrow, bn * xrow * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+        DR_CUDA(m, cudaEventRecord(m->ev_pipe[c], m->copy_stream));
+    }
+    for (int c = 0; c < nc; ++c) {
+        int b0 = c * Bc, bn = (c == nc - 1) ? B - b0 : Bc;
+        DR_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_pipe[c], 0));
+        rc = dr_forward_dev(m, m->d_xin + b0 * xrow, bn, T, m->d_out + b0 * orow);
+        if (rc != DR_OK) return rc;
+        DR_CUDA(m, cudaEventRecord(m->ev_pipe[2 + c], m->stream));
+        DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[2 + c], 0));
+        DR_CUDA(m, cudaMemcpyAsync(out + b0 * orow, m->d_out + b0 * orow, bn * orow * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
+    }
+    DR_CUDA(m, cudaStreamSynchronize(m->copy_stream));
     DR_CUDA(m, cudaStreamSynchronize(m->stream));
     return DR_OK;
 }

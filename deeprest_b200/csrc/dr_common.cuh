@@ -72,6 +72,8 @@ struct dr_model {
 
     cudaStream_t stream;
     cudaStream_t own_stream;
+    cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
+    cudaEvent_t ev_pipe[5];
     int64_t launches;
     bool profile;
     int prof_n;                     // forwards recorded since dr_profile(m,1)

@@ -182,13 +182,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     const float4 cr = *reinterpret_cast<const float4*>(bs + u0 + j4);
                     const float4 cz = *reinterpret_cast<const float4*>(bs + DR_H + u0 + j4);
                     const float4 cn = *reinterpret_cast<const float4*>(bs + 2 * DR_H + u0 + j4);
-                    const float4 h0c = *reinterpret_cast<const float4*>(cs + u0 + j4);
-                    const float4 h1c = *reinterpret_cast<const float4*>(cs + DR_H + u0 + j4);
-                    const float4 h2c = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0 + j4);
                     const float crv[4] = {cr.x, cr.y, cr.z, cr.w}, czv[4] = {cz.x, cz.y, cz.z, cz.w};
                     const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
-                    const float c0v[4] = {h0c.x, h0c.y, h0c.z, h0c.w}, c1v[4] = {h1c.x, h1c.y, h1c.z, h1c.w};
-                    const float c2v[4] = {h2c.x, h2c.y, h2c.z, h2c.w};
                     float rr[4], zz[4], pn[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -215,9 +210,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
                         hreg[q][j] = a0; hreg[q][j + 1] = a1;
                         hn[j] = a0; hn[j + 1] = a1;
-                        o0 = fmaf(c0v[i], a0, o0); o0 = fmaf(c0v[i + 1], a1, o0);
-                        o1 = fmaf(c1v[i], a0, o1); o1 = fmaf(c1v[i + 1], a1, o1);
-                        o2 = fmaf(c2v[i], a0, o2); o2 = fmaf(c2v[i + 1], a1, o2);
                         // fp16 split of the pair with packed conversions (F2FP / HADD2.F32: no XU-pipe traffic)
                         __half2 hi2 = __floats2half2_rn(a0, a1);
                         float2 back = __half22float2(hi2);
@@ -232,6 +224,16 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(bar(H_READY0 + q), 0);   // K columns [32q, 32q+32) of h_t are in TMEM
+                // off the critical path (the next MMAs only need the TMEM copy of h): own-expert head dot, S reduction
+#pragma unroll
+                for (int j4 = 0; j4 < 16; j4 += 4) {
+                    const float4 c0 = *reinterpret_cast<const float4*>(cs + u0 + j4);
+                    const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0 + j4);
+                    const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0 + j4);
+                    o0 = fmaf(c0.x, hn[j4], o0); o0 = fmaf(c0.y, hn[j4 + 1], o0); o0 = fmaf(c0.z, hn[j4 + 2], o0); o0 = fmaf(c0.w, hn[j4 + 3], o0);
+                    o1 = fmaf(c1.x, hn[j4], o1); o1 = fmaf(c1.y, hn[j4 + 1], o1); o1 = fmaf(c1.z, hn[j4 + 2], o1); o1 = fmaf(c1.w, hn[j4 + 3], o1);
+                    o2 = fmaf(c2.x, hn[j4], o2); o2 = fmaf(c2.y, hn[j4 + 1], o2); o2 = fmaf(c2.z, hn[j4 + 2], o2); o2 = fmaf(c2.w, hn[j4 + 3], o2);
+                }
                 if (live) {
                     float* sp = S + (((size_t)tt * 64 + dir * 32 + u0 / 4) * Bp + b) * 4;
 #pragma unroll
