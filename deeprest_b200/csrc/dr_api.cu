@@ -80,7 +80,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wtc = nullptr; m->wtc_bytes = 0;
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
-    m->copy_stream = nullptr;
+    m->copy_stream = nullptr; m->d_tc_dbg = nullptr;
     for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
@@ -115,7 +115,7 @@ void dr_destroy(dr_model* m) {
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
-    void* ptrs[] = {m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+    void* ptrs[] = {m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->d_xT, m->d_xtc, m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -353,6 +353,19 @@ int dr_debug_read(dr_model* m, const char* what, float* host, size_t n) {
     if (check_handle(m)) return DR_EINVAL;
     if (!what || !host) return dr_fail(m, DR_EINVAL, "null argument");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    if (!strcmp(what, "tc_timing_on")) {          // enable the in-kernel cycle breakdown (host_buf unused)
+        if (!m->d_tc_dbg) { DR_CUDA(m, cudaMalloc((void**)&m->d_tc_dbg, 32 * sizeof(unsigned long long))); }
+        DR_CUDA(m, cudaMemset(m->d_tc_dbg, 0, 32 * sizeof(unsigned long long)));
+        return DR_OK;
+    }
+    if (!strcmp(what, "tc_timing")) {             // 18 counters as floats (cycles), see dr_gru_tc.cu
+        if (!m->d_tc_dbg || n < 18) return dr_fail(m, DR_EINVAL, "tc_timing: enable with tc_timing_on first; needs 18 floats");
+        unsigned long long h[32];
+        DR_CUDA(m, cudaStreamSynchronize(m->stream));
+        DR_CUDA(m, cudaMemcpy(h, m->d_tc_dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 18; ++i) host[i] = (float)h[i];
+        return DR_OK;
+    }
     const float* src = nullptr; size_t avail = 0;
     if (!strcmp(what, "mask")) { src = m->d_mask; avail = (size_t)m->M_loc * m->cfg.F; }
     else if (!strcmp(what, "S")) { src = m->d_S; avail = m->S_cap / sizeof(float); }

@@ -72,6 +72,7 @@ struct dr_model {
 
     cudaStream_t stream;
     cudaStream_t own_stream;
+    unsigned long long* d_tc_dbg;   // optional cycle breakdown of the tcgen05 kernel (dr_debug_read "tc_timing")
     cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
     cudaEvent_t ev_pipe[5];
     int64_t launches;

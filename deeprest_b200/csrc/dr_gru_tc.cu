@@ -31,7 +31,7 @@ using namespace drtc;
 
 namespace {
 
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;          // 3 warpgroups: 2 x epilogue (warps 0-7), 1 x {MMA issuer, producer, 2 idle}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = 8, kLoadWarp = 9;
@@ -68,6 +68,7 @@ __device__ __forceinline__ void store_bhn(uint32_t taddr, const float* src) {
     tmem_st8(taddr + 8, v1);
 }
 
+template <bool kTiming>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][kWBytes]
                  const uint8_t* __restrict__ xtc,     // [T][ntiles][2 cta][hi|lo][kXTile]
@@ -75,7 +76,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                  const float* __restrict__ ct,        // [M_loc][2][Q][H]
                  float* __restrict__ S,               // [T][64][Bp][4]
                  float* __restrict__ out_local,       // [B][T][M_loc][Q]
-                 int B, int T, int Bp, int M_loc, int ntiles) {
+                 int B, int T, int Bp, int M_loc, int ntiles,
+                 unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta = cluster_ctarank();
@@ -113,6 +115,13 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
 
+    // Register re-partition (setmaxnreg, per warpgroup): the launch gives every thread 168 registers; the third
+    // warpgroup (MMA issuer, producer, two idle warps) keeps 72 and the two epilogue warpgroups grow to 216 (2*128*216 + 128*72 = the 384*168 registers of the launch), which
+    // removes the spills ptxas needed at 168 (ncu r01c: LDL long-scoreboard stalls inside the gate math).
+    // (setmaxnreg is warpgroup-collective: every warp of a warpgroup executes the SAME instruction, hence before the
+    //  per-warp role dispatch.)
+    if (warp < kEpiWarps) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    else                  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp < kEpiWarps) {
         // ======================= gate epilogue warps =======================
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -150,19 +159,59 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
 #pragma unroll
             for (int j = 0; j < 16; ++j) hreg[q][j] = 0.0f;
 
+        const bool timing = kTiming && dbg != nullptr && item == 0 && cta == 0 && warp == 0 && lane == 0;
+        long long t_wait[4] = {0, 0, 0, 0}, t_ld = 0, t_math = 0, t_tail = 0;
+        const long long t_begin = clock64();
         uint32_t full_phase[2] = {0, 0};
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+        float hn[16];
+        // Work that is off the recurrence's critical path — the own-expert head dot and the RED of h into S — for the 16
+        // hidden units starting at u0p of time step ttp.  The two warps that share an SM sub-partition (half 0 / half 1) run
+        // it at different points of the quarter so that one warp's MUFU-bound gate math overlaps the other's FMA/LSU work:
+        // half 0 right after its gate math, half 1 one quarter later, just before its next gate math (clock64 breakdown:
+        // in lock-step both warps contend for the 16-lane XU pipe during the math and leave it idle during this part).
+        auto tail = [&](int u0p, int ttp) {
+            float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+                const float4 c0 = *reinterpret_cast<const float4*>(cs + u0p + j4);
+                const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0p + j4);
+                const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0p + j4);
+                p0[0] = fmaf(c0.x, hn[j4], p0[0]); p0[1] = fmaf(c0.y, hn[j4 + 1], p0[1]); p0[2] = fmaf(c0.z, hn[j4 + 2], p0[2]); p0[3] = fmaf(c0.w, hn[j4 + 3], p0[3]);
+                p1[0] = fmaf(c1.x, hn[j4], p1[0]); p1[1] = fmaf(c1.y, hn[j4 + 1], p1[1]); p1[2] = fmaf(c1.z, hn[j4 + 2], p1[2]); p1[3] = fmaf(c1.w, hn[j4 + 3], p1[3]);
+                p2[0] = fmaf(c2.x, hn[j4], p2[0]); p2[1] = fmaf(c2.y, hn[j4 + 1], p2[1]); p2[2] = fmaf(c2.z, hn[j4 + 2], p2[2]); p2[3] = fmaf(c2.w, hn[j4 + 3], p2[3]);
+            }
+            o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
+            o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
+            o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
+            if (live) {
+                float* sp = S + (((size_t)ttp * 64 + dir * 32 + u0p / 4) * Bp + b) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dr_red_add_v4(sp + (size_t)j * Bp * 4, hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+            }
+        };
+        auto flush = [&](int ttp) {          // the step's own-expert head term is complete: out_local[b,ttp,e,:] += o
+            if (live) {
+                float* o = out_local + (((size_t)b * T + ttp) * M_loc + e) * DR_Q;
+                dr_red_add(o, o0); dr_red_add(o + 1, o1); dr_red_add(o + 2, o2);
+            }
+            o0 = 0.f; o1 = 0.f; o2 = 0.f;
+        };
         for (int s = 0; s < T; ++s) {
             const int tt = dir ? (T - 1 - s) : s;
+            const int tt_prev = dir ? (T - s) : (s - 1);
             const uint32_t hnext = (s & 1) ? kHA : kHB;           // step s reads (s&1 ? HB : HA), writes the other
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int buf = q & 1;
                 const int u0 = q * 32 + half * 16;                // first hidden unit handled here
                 const uint32_t G = tbase + lane_base + kG0 + buf * 128 + half * 16;
+                const long long tq0 = timing ? clock64() : 0;
                 mbar_wait(bar(GATE_FULL0 + buf), full_phase[buf]);
                 full_phase[buf] ^= 1;
                 tc_fence_after();
+                const long long tq1 = timing ? clock64() : 0;
                 uint32_t gi[16], gr[16], gz[16], gh[16];
                 tmem_ld16(G + 0, gi); tmem_ld16(G + 32, gr); tmem_ld16(G + 64, gz); tmem_ld16(G + 96, gh);
                 tc_wait_ld();
@@ -175,39 +224,70 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(bar(GATE_FREE0 + buf), 0);
                 }
+                const long long tq2 = timing ? clock64() : 0;
+                if (half == 1 && (s > 0 || q > 0)) {              // lagging warp: previous quarter's tail first
+                    tail(((q + 3) & 3) * 32 + 16, q == 0 ? tt_prev : tt);
+                    if (q == 0) flush(tt_prev);
+                }
                 uint32_t phi[8], plo[8];
-                float hn[16];
+                // Stage-major over 8 cells at a time: each stage's instructions are independent of one another, so one warp
+                // keeps the XU (MUFU) pipe and the FMA pipe busy by itself (ncu/clock64: the per-cell order was latency bound).
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const float4 cr = *reinterpret_cast<const float4*>(bs + u0 + j4);
-                    const float4 cz = *reinterpret_cast<const float4*>(bs + DR_H + u0 + j4);
-                    const float4 cn = *reinterpret_cast<const float4*>(bs + 2 * DR_H + u0 + j4);
-                    const float crv[4] = {cr.x, cr.y, cr.z, cr.w}, czv[4] = {cz.x, cz.y, cz.z, cz.w};
-                    const float cnv[4] = {cn.x, cn.y, cn.z, cn.w};
-                    float rr[4], zz[4], pn[4];
+                for (int j8 = 0; j8 < 16; j8 += 8) {
+                    float cr[8], cz[8], cn[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int j = j4 + i;
-                        // r, z = sigmoid(.) with ONE shared reciprocal: 1/((1+er)(1+ez))
-                        float er = ex2_approx(fminf(fmaf(__uint_as_float(gr[j]), -kLog2e, crv[i]), 40.0f));
-                        float ez = ex2_approx(fminf(fmaf(__uint_as_float(gz[j]), -kLog2e, czv[i]), 40.0f));
-                        float pr = 1.0f + er, pz = 1.0f + ez;
-                        float inv = rcp_approx(pr * pz);
-                        rr[i] = pz * inv;
-                        zz[i] = pr * inv;
-                        // n = tanh(gi_n + b_in + r*(gh_n + b_hn)) = 1 - 2/(1 + exp(2t));  b_hn is already in gh
-                        float t = fmaf(rr[i], __uint_as_float(gh[j]), __uint_as_float(gi[j]));
-                        pn[i] = 1.0f + ex2_approx(fminf(fmaf(t, 2.0f * kLog2e, cnv[i]), 40.0f));
+                    for (int v = 0; v < 2; ++v) {
+                        const float4 a = *reinterpret_cast<const float4*>(bs + u0 + j8 + 4 * v);
+                        const float4 b4 = *reinterpret_cast<const float4*>(bs + DR_H + u0 + j8 + 4 * v);
+                        const float4 c = *reinterpret_cast<const float4*>(bs + 2 * DR_H + u0 + j8 + 4 * v);
+                        cr[4 * v] = a.x; cr[4 * v + 1] = a.y; cr[4 * v + 2] = a.z; cr[4 * v + 3] = a.w;
+                        cz[4 * v] = b4.x; cz[4 * v + 1] = b4.y; cz[4 * v + 2] = b4.z; cz[4 * v + 3] = b4.w;
+                        cn[4 * v] = c.x; cn[4 * v + 1] = c.y; cn[4 * v + 2] = c.z; cn[4 * v + 3] = c.w;
+                    }
+                    float er[8], ez[8], rr[8], zz[8], pn[8];
+                    // r, z = sigmoid(.): exp via ex2, and ONE reciprocal per two cells: 1/((1+er0)(1+ez0)(1+er1)(1+ez1)).
+                    // Arguments are clamped at 2^30 so that four factors cannot overflow (sigmoid error < 1e-9 there).
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        er[i] = fminf(fmaf(__uint_as_float(gr[j8 + i]), -kLog2e, cr[i]), 30.0f);
+                        ez[i] = fminf(fmaf(__uint_as_float(gz[j8 + i]), -kLog2e, cz[i]), 30.0f);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; i += 2) {                  // tanh pairs share a reciprocal
-                        const int j = j4 + i;
-                        float inv = rcp_approx(pn[i] * pn[i + 1]);
-                        float n0 = fmaf(-2.0f * pn[i + 1], inv, 1.0f);
-                        float n1 = fmaf(-2.0f * pn[i], inv, 1.0f);
+                    for (int i = 0; i < 8; ++i) { er[i] = ex2_approx(er[i]); ez[i] = ex2_approx(ez[i]); }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { er[i] += 1.0f; ez[i] += 1.0f; rr[i] = er[i] * ez[i]; }
+                    float iv2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) iv2[i] = rcp_approx(rr[2 * i] * rr[2 * i + 1]);
+                    // n = tanh(gi_n + b_in + r*(gh_n + b_hn)) = 1 - 2/(1 + exp(2t));  b_hn is already in gh
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float inv = rr[i ^ 1] * iv2[i >> 1];          // 1/((1+er_i)(1+ez_i))
+                        zz[i] = er[i] * inv;
+                        const float r_i = ez[i] * inv;
+                        const float t = fmaf(r_i, __uint_as_float(gh[j8 + i]), __uint_as_float(gi[j8 + i]));
+                        pn[i] = fminf(fmaf(t, 2.0f * kLog2e, cn[i]), 30.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pn[i] = ex2_approx(pn[i]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) pn[i] += 1.0f;
+                    float ivn[4];                                             // 1/(pn[2i]*pn[2i+1]) from ONE reciprocal per four cells
+#pragma unroll
+                    for (int g4 = 0; g4 < 2; ++g4) {
+                        const float pa = pn[4 * g4] * pn[4 * g4 + 1], pb = pn[4 * g4 + 2] * pn[4 * g4 + 3];
+                        const float inv4 = rcp_approx(pa * pb);
+                        ivn[2 * g4] = pb * inv4;
+                        ivn[2 * g4 + 1] = pa * inv4;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const int j = j8 + i;
+                        const float n0 = fmaf(-2.0f * pn[i + 1], ivn[i >> 1], 1.0f);
+                        const float n1 = fmaf(-2.0f * pn[i], ivn[i >> 1], 1.0f);
                         // h' = (1-z)*n + z*h, evaluated as torch's CPU cell does: (h - n)*z + n
-                        float a0 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j], n0), zz[i]), n0);
-                        float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
+                        const float a0 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j], n0), zz[i]), n0);
+                        const float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
                         hreg[q][j] = a0; hreg[q][j + 1] = a1;
                         hn[j] = a0; hn[j + 1] = a1;
                         // fp16 split of the pair with packed conversions (F2FP / HADD2.F32: no XU-pipe traffic)
@@ -224,27 +304,19 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(bar(H_READY0 + q), 0);   // K columns [32q, 32q+32) of h_t are in TMEM
-                // off the critical path (the next MMAs only need the TMEM copy of h): own-expert head dot, S reduction
-#pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const float4 c0 = *reinterpret_cast<const float4*>(cs + u0 + j4);
-                    const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0 + j4);
-                    const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0 + j4);
-                    o0 = fmaf(c0.x, hn[j4], o0); o0 = fmaf(c0.y, hn[j4 + 1], o0); o0 = fmaf(c0.z, hn[j4 + 2], o0); o0 = fmaf(c0.w, hn[j4 + 3], o0);
-                    o1 = fmaf(c1.x, hn[j4], o1); o1 = fmaf(c1.y, hn[j4 + 1], o1); o1 = fmaf(c1.z, hn[j4 + 2], o1); o1 = fmaf(c1.w, hn[j4 + 3], o1);
-                    o2 = fmaf(c2.x, hn[j4], o2); o2 = fmaf(c2.y, hn[j4 + 1], o2); o2 = fmaf(c2.z, hn[j4 + 2], o2); o2 = fmaf(c2.w, hn[j4 + 3], o2);
-                }
-                if (live) {
-                    float* sp = S + (((size_t)tt * 64 + dir * 32 + u0 / 4) * Bp + b) * 4;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dr_red_add_v4(sp + (size_t)j * Bp * 4, hn[4 * j], hn[4 * j + 1], hn[4 * j + 2], hn[4 * j + 3]);
+                const long long tq3 = timing ? clock64() : 0;
+                if (half == 0) { tail(u0, tt); if (q == 3) flush(tt); }
+                if (timing) {
+                    const long long tq4 = clock64();
+                    t_wait[q] += tq1 - tq0; t_ld += tq2 - tq1; t_math += tq3 - tq2; t_tail += tq4 - tq3;
                 }
             }
-            if (live) {
-                float* o = out_local + (((size_t)b * T + tt) * M_loc + e) * DR_Q;
-                dr_red_add(o, o0); dr_red_add(o + 1, o1); dr_red_add(o + 2, o2);
-            }
+        }
+        if (half == 1) { const int tl = dir ? 0 : (T - 1); tail(3 * 32 + 16, tl); flush(tl); }
+        if (timing) {
+            dbg[0] = (unsigned long long)(clock64() - t_begin);
+            for (int q = 0; q < 4; ++q) dbg[1 + q] = (unsigned long long)t_wait[q];
+            dbg[5] = (unsigned long long)t_ld; dbg[6] = (unsigned long long)t_math; dbg[7] = (unsigned long long)t_tail;
         }
     } else if (warp == kMmaWarp) {
         // ======================= MMA issuer (leader CTA only) =======================
@@ -253,17 +325,29 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
             const uint32_t w_s = smem_u32(smem + kOffW);
             const uint32_t x_s = smem_u32(smem + kOffX);
             mbar_wait_cluster(bar(W_READY), 0);
-            uint32_t free_phase[2] = {0, 0};
+            const bool mt = kTiming && dbg != nullptr && item == 0;
+            long long m_x = 0, m_free[4] = {0, 0, 0, 0}, m_h[4] = {0, 0, 0, 0};
+            const long long m_begin = clock64();
+            uint32_t free_bits = 0;                    // bit b = phase parity of GATE_FREE[b]
             for (int s = 0; s < T; ++s) {
                 const uint32_t hcur = tbase + ((s & 1) ? kHB : kHA);
                 const uint32_t xst = x_s + (s & 1) * kXStage;
-                mbar_wait_cluster(bar(X_FULL0 + (s & 1)), (s >> 1) & 1);
+                { const long long a = mt ? clock64() : 0;
+                  mbar_wait_cluster(bar(X_FULL0 + (s & 1)), (s >> 1) & 1);
+                  if (mt) m_x += clock64() - a; }
+                const uint64_t xdesc = make_desc_sw128(xst);
+#pragma unroll 1
                 for (int q = 0; q < 4; ++q) {
                     const int buf = q & 1;
                     const uint32_t G = tbase + kG0 + buf * 128;
                     const uint32_t wq = w_s + q * kQuarterBytes;
-                    mbar_wait_cluster(bar(GATE_FREE0 + buf), free_phase[buf]);
-                    free_phase[buf] ^= 1;
+                    // descriptors: one base per operand tile; every other one is base + (byte offset >> 4) in the 14-bit
+                    // start-address field (shared memory < 256 KB, so the field cannot carry out)
+                    const uint64_t wdesc = make_desc_sw128(wq);
+                    { const long long a = mt ? clock64() : 0;
+                      mbar_wait_cluster(bar(GATE_FREE0 + buf), (free_bits >> buf) & 1u);
+                      if (mt) m_free[q] += clock64() - a; }
+                    free_bits ^= 1u << buf;
                     tc_fence_after();
                     // x-part: (hi,hi) (hi,lo) (lo,hi);  A parts at xst + {0, kXTile}, B parts at wq + {0, kBlk}
 #pragma unroll
@@ -272,7 +356,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         const uint32_t bb = wq + (term == 1 ? kBlk : 0);
 #pragma unroll
                         for (int k16 = 0; k16 < 4; ++k16)
-                            mma_ss<2>(G, make_desc_sw128(ab + k16 * 32), make_desc_sw128(bb + k16 * 32), idesc,
+                            mma_ss<2>(G, xdesc + ((ab - xst + k16 * 32) >> 4), wdesc + ((bb - wq + k16 * 32) >> 4), idesc,
                                       (term | k16) ? 1u : 0u);
                     }
                     // h-part: A from TMEM (hi at hcur, lo at hcur+64), B blocks Wh_hi[kb] at wq+2*kBlk, Wh_lo[kb] at wq+4*kBlk.
@@ -281,7 +365,12 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     // end of the previous step's epilogue.
 #pragma unroll
                     for (int kq = 0; kq < 4; ++kq) {
-                        if (q == 0) { mbar_wait_cluster(bar(H_READY0 + kq), s & 1); tc_fence_after(); }
+                        if (q == 0) {
+                            const long long a = mt ? clock64() : 0;
+                            mbar_wait_cluster(bar(H_READY0 + kq), s & 1);
+                            if (mt) m_h[kq] += clock64() - a;
+                            tc_fence_after();
+                        }
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
                             const uint32_t at = hcur + (term == 2 ? 64 : 0);
@@ -290,7 +379,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                             for (int j = 0; j < 2; ++j) {
                                 const int ks = kq * 2 + j, kb = ks >> 2, k16 = ks & 3;
                                 mma_ts<2>(G + 32, at + (kb * 64 + k16 * 16) / 2,
-                                          make_desc_sw128(bb + kb * kBlk + k16 * 32), idesc, 1u);
+                                          wdesc + ((bb - wq + kb * kBlk + k16 * 32) >> 4), idesc, 1u);
                             }
                         }
                     }
@@ -298,11 +387,15 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 }
                 mma_commit_2(bar(X_FREE0 + (s & 1)), 0x3);
             }
+            if (mt) {
+                dbg[8] = (unsigned long long)(clock64() - m_begin); dbg[9] = (unsigned long long)m_x;
+                for (int q = 0; q < 4; ++q) { dbg[10 + q] = (unsigned long long)m_free[q]; dbg[14 + q] = (unsigned long long)m_h[q]; }
+            }
         }
         __syncwarp();
     } else {
-        // ======================= bulk-copy producer =======================
-        if (elect_one()) {
+        // ======================= bulk-copy producer (warp 9; warps 10-11 only donate their registers) =======================
+        if (warp == kLoadWarp && elect_one()) {
             const uint8_t* wsrc = wtc + ((size_t)(e * 2 + dir) * 2 + cta) * kWBytes;
             mbar_expect_tx(bar(W_LAND), kWBytes);
 #pragma unroll
@@ -440,13 +533,19 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
         dr_tc_pack_x_kernel<<<blocks, 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), B, T, m->cfg.F, ntiles);
         DR_CUDA(m, cudaGetLastError());
     }
-    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     int items = m->M_loc * 2 * ntiles;
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
-    dr_gru_tc_kernel<<<items * 2, kThreads, kSmemBytes, m->stream>>>(
-        reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-        S, out_local, B, T, Bp, m->M_loc, ntiles);
+    if (m->d_tc_dbg)
+        dr_gru_tc_kernel<true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+            reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
+            S, out_local, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg);
+    else
+        dr_gru_tc_kernel<false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+            reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
+            S, out_local, B, T, Bp, m->M_loc, ntiles, nullptr);
     DR_CUDA(m, cudaGetLastError());
     if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
     m->launches += 2;
