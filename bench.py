@@ -334,7 +334,7 @@ def run_ours(args, rank, world, local_rank):
         "algorithmic_flops_per_launch": flops,
         "algorithmic_hbm_bytes_per_launch": algorithmic_hbm_bytes(M_loc, M, B, T, F),
         "hbm_gbs_if_ideal_bytes": algorithmic_hbm_bytes(M_loc, M, B, T, F) / (gru_ms * 1e-3) / 1e9 if gru_ms > 0 else None,
-        "note": ("fp32 parity needs split-bf16 operands: the tcgen05 engine issues 3 tensor passes per "
+        "note": ("fp32 parity needs split-fp16 operands: the tcgen05 engine issues 3 tensor passes per "
                  "algorithmic FLOP, so frac <= 1/3 by construction; the FFMA engine runs on CUDA cores")
     }
 
