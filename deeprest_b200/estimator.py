@@ -174,17 +174,21 @@ class QuantileRNN:
         from .sharding import sharded_forward
         lib, h = self._lib, self._h
 
+        # each phase binds the handle to the stream it is called on (the exchange runs on a side stream)
         def local_fn(xx, S, out_local):
-            _lib.check(h, lib.dr_forward_local_dev(h, xx.data_ptr(), B, T, S.data_ptr(), out_local.data_ptr()))
+            self._bind_stream()
+            _lib.check(h, lib.dr_forward_local_dev(h, xx.data_ptr(), xx.shape[0], T, S.data_ptr(), out_local.data_ptr()))
 
         def heads_fn(S, out_local):
-            _lib.check(h, lib.dr_forward_heads_dev(h, S.data_ptr(), B, T, out_local.data_ptr()))
+            self._bind_stream()
+            _lib.check(h, lib.dr_forward_heads_dev(h, S.data_ptr(), out_local.shape[0], T, out_local.data_ptr()))
 
         def interleave_fn(gathered, out):
-            _lib.check(h, lib.dr_interleave_dev(h, gathered.data_ptr(), B, T, out.data_ptr()))
+            self._bind_stream()
+            _lib.check(h, lib.dr_interleave_dev(h, gathered.data_ptr(), out.shape[0], T, out.data_ptr()))
 
         return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
-                               s_elems=lib.dr_s_elems(B, T), local_fn=local_fn, heads_fn=heads_fn,
+                               s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
                                interleave_fn=interleave_fn, group=self._pg)
 
     # ---- training ----------------------------------------------------------------------

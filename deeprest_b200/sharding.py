@@ -6,24 +6,63 @@ the buffers live on (NCCL over NVLink on the GPUs; gloo in the CPU tests).  The 
 phases are callables so the same orchestration is exercised by ``tests/test_sharding_gloo.py``
 without a GPU (there the callables are oracle code; in the product they are the C-ABI phases
 ``dr_forward_local_dev`` / ``dr_forward_heads_dev`` / ``dr_interleave_dev``).
+
+On CUDA the batch is cut into chunks of whole 256-window pair tiles and the exchange of chunk c
+(all-reduce, heads, all-gather, interleave — on a high-priority side stream) overlaps the
+recurrence kernel of chunk c+1 on the caller's stream: windows are independent, so this is exact.
 """
 from __future__ import annotations
 
+_side_streams = {}
+
+
+def _chunks(B, is_cuda):
+    if not is_cuda or B < 512:
+        return [(0, B)]
+    n = max(2, min(4, B // 256))
+    step = ((B + n - 1) // n + 255) // 256 * 256
+    return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
+
 
 def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interleave_fn, group=None):
-    """x [B,T,F] (replicated on every rank) -> forecasts [B,T,world*m_local,q] on every rank."""
+    """x [B,T,F] (replicated on every rank) -> forecasts [B,T,world*m_local,q] on every rank.
+
+    local_fn(x_c, S_c, out_local_c), heads_fn(S_c, out_local_c), interleave_fn(gathered_c, out_c) act on
+    a chunk of windows; s_elems(bn) gives the size of S for bn windows."""
     import torch
     import torch.distributed as dist
 
     B, T = int(x.shape[0]), int(x.shape[1])
-    S = torch.empty((int(s_elems),), device=x.device, dtype=torch.float32)
-    out_local = torch.empty((B, T, m_local, q), device=x.device, dtype=torch.float32)
-    local_fn(x, S, out_local)                                   # local bi-GRUs: partial S, own-expert head term
-    dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)       # head i needs every other expert's output
-    heads_fn(S, out_local)                                      # + (A_i/(M-1))·S + b_i
-    flat = torch.empty((world * B, T, m_local, q), device=x.device, dtype=torch.float32)
-    dist.all_gather_into_tensor(flat, out_local, group=group)   # rank-major concatenation along dim 0
-    gathered = flat.view(world, B, T, m_local, q)
     out = torch.empty((B, T, world * m_local, q), device=x.device, dtype=torch.float32)
-    interleave_fn(gathered, out)                                # [w][B,T,M/w,Q] -> reference layout [B,T,M,Q]
+    chunks = _chunks(B, x.is_cuda)
+    overlap = x.is_cuda and len(chunks) > 1
+    if overlap:
+        main = torch.cuda.current_stream(x.device)
+        side = _side_streams.get(x.device)
+        if side is None:
+            side = _side_streams[x.device] = torch.cuda.Stream(device=x.device, priority=-1)
+    for b0, b1 in chunks:
+        bn = b1 - b0
+        S = torch.empty((int(s_elems(bn)),), device=x.device, dtype=torch.float32)
+        out_local = torch.empty((bn, T, m_local, q), device=x.device, dtype=torch.float32)
+        flat = torch.empty((world * bn, T, m_local, q), device=x.device, dtype=torch.float32)
+        local_fn(x[b0:b1], S, out_local)                           # local bi-GRUs: partial S, own-expert head term
+
+        def exchange():
+            dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)  # head i needs every other expert's output
+            heads_fn(S, out_local)                                 # + (A_i/(M-1))·S + b_i
+            dist.all_gather_into_tensor(flat, out_local, group=group)   # rank-major concatenation along dim 0
+            interleave_fn(flat.view(world, bn, T, m_local, q), out[b0:b1])   # -> reference layout [B,T,M,Q]
+
+        if overlap:
+            ev = main.record_event()
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                exchange()
+            for t in (S, out_local, flat):
+                t.record_stream(side)
+        else:
+            exchange()
+    if overlap:
+        main.wait_stream(side)
     return out

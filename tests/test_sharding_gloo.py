@@ -34,23 +34,22 @@ def _worker(rank, world, port, result_path):
         m_local = M // world
         lo, hi = rank * m_local, (rank + 1) * m_local
         experts = layout.unpack_blob(blob, M, F)[lo:hi]
-        r_local = [oracle.expert_rnn_out(ex, x) for ex in experts]          # [B,T,2H] each
-
         def local_fn(xx, S, out_local):
+            r_local = [oracle.expert_rnn_out(ex, xx.numpy()) for ex in experts]          # [bn,T,2H] each
             S.copy_(torch.from_numpy(sum(r_local).reshape(-1)))
             own = np.stack([r @ (ex["head_w"][:, 2 * H:] - ex["head_w"][:, :2 * H] / (M - 1)).T
                             for r, ex in zip(r_local, experts)], axis=2)     # (C - A/(M-1))·r_i
             out_local.copy_(torch.from_numpy(own.astype(np.float32)))
 
         def heads_fn(S, out_local):
-            Sn = S.numpy().reshape(B, T, 2 * H)
+            Sn = S.numpy().reshape(out_local.shape[0], T, 2 * H)
             add = np.stack([Sn @ (ex["head_w"][:, :2 * H] / (M - 1)).T + ex["head_b"] for ex in experts], axis=2)
             out_local.add_(torch.from_numpy(add.astype(np.float32)))
 
         def interleave_fn(gathered, out):
-            out.copy_(gathered.permute(1, 2, 0, 3, 4).reshape(B, T, world * m_local, Q))
+            out.copy_(gathered.permute(1, 2, 0, 3, 4).reshape(out.shape[0], T, world * m_local, Q))
 
-        out = sharded_forward(torch.from_numpy(x), world=world, m_local=m_local, q=Q, s_elems=B * T * 2 * H,
+        out = sharded_forward(torch.from_numpy(x), world=world, m_local=m_local, q=Q, s_elems=lambda bn: bn * T * 2 * H,
                               local_fn=local_fn, heads_fn=heads_fn, interleave_fn=interleave_fn)
         ref = oracle.forward(blob, x, M, F)
         err = float(np.abs(out.numpy() - ref).max())
@@ -76,3 +75,12 @@ def test_expert_shards_are_equal_and_cover():
         M_ = 2048
         spans = [(r * (M_ // world), (r + 1) * (M_ // world)) for r in range(world)]
         assert spans[0][0] == 0 and spans[-1][1] == M_
+
+
+def test_chunk_plan_covers_the_batch_in_pair_tiles():
+    from deeprest_b200.sharding import _chunks
+    assert _chunks(300, True) == [(0, 300)] and _chunks(4096, False) == [(0, 4096)]
+    for B in (512, 1024, 1000, 4096, 777):
+        ch = _chunks(B, True)
+        assert ch[0][0] == 0 and ch[-1][1] == B and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all((b1 - b0) % 256 == 0 for b0, b1 in ch[:-1]) and 2 <= len(ch) <= 4
