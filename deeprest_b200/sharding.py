@@ -7,9 +7,11 @@ phases are callables so the same orchestration is exercised by ``tests/test_shar
 without a GPU (there the callables are oracle code; in the product they are the C-ABI phases
 ``dr_forward_local_dev`` / ``dr_forward_heads_dev`` / ``dr_interleave_dev``).
 
-On CUDA the batch is cut into chunks of whole 256-window pair tiles and the exchange of chunk c
-(all-reduce, heads, all-gather, interleave — on a high-priority side stream) overlaps the
-recurrence kernel of chunk c+1 on the caller's stream: windows are independent, so this is exact.
+On CUDA the batch is cut into chunks of whole 256-window pair tiles and each chunk's pipeline
+(recurrence, all-reduce, heads, all-gather, interleave) runs on one of two alternating side
+streams: the exchange of chunk c overlaps the recurrence kernel of chunk c+1, and the CTAs of
+chunk c+1's recurrence fill the SMs that chunk c's last wave leaves idle.  Windows are
+independent, so this is exact.  (The library keeps 4 operand-image workspace slots for this.)
 """
 from __future__ import annotations
 
@@ -38,31 +40,33 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
     overlap = x.is_cuda and len(chunks) > 1
     if overlap:
         main = torch.cuda.current_stream(x.device)
-        side = _side_streams.get(x.device)
-        if side is None:
-            side = _side_streams[x.device] = torch.cuda.Stream(device=x.device, priority=-1)
-    for b0, b1 in chunks:
+        sides = _side_streams.get(x.device)
+        if sides is None:
+            sides = _side_streams[x.device] = [torch.cuda.Stream(device=x.device) for _ in range(2)]
+        start = main.record_event()
+    for c, (b0, b1) in enumerate(chunks):
         bn = b1 - b0
         S = torch.empty((int(s_elems(bn)),), device=x.device, dtype=torch.float32)
         out_local = torch.empty((bn, T, m_local, q), device=x.device, dtype=torch.float32)
         flat = torch.empty((world * bn, T, m_local, q), device=x.device, dtype=torch.float32)
-        local_fn(x[b0:b1], S, out_local)                           # local bi-GRUs: partial S, own-expert head term
 
-        def exchange():
+        def pipeline():
+            local_fn(x[b0:b1], S, out_local)                       # local bi-GRUs: partial S, own-expert head term
             dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)  # head i needs every other expert's output
             heads_fn(S, out_local)                                 # + (A_i/(M-1))·S + b_i
             dist.all_gather_into_tensor(flat, out_local, group=group)   # rank-major concatenation along dim 0
             interleave_fn(flat.view(world, bn, T, m_local, q), out[b0:b1])   # -> reference layout [B,T,M,Q]
 
         if overlap:
-            ev = main.record_event()
+            side = sides[c % 2]
             with torch.cuda.stream(side):
-                side.wait_event(ev)
-                exchange()
-            for t in (S, out_local, flat):
+                side.wait_event(start)
+                pipeline()
+            for t in (S, out_local, flat, out, x):
                 t.record_stream(side)
         else:
-            exchange()
+            pipeline()
     if overlap:
-        main.wait_stream(side)
+        for side in sides:
+            main.wait_stream(side)
     return out
