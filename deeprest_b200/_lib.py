@@ -42,6 +42,10 @@ SIGNATURES = {
     "dr_get_weights": (C.c_int, [_H, _FP, C.c_size_t]),
     "dr_forward": (C.c_int, [_H, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_forward_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dr_series_windows": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "dr_forward_series": (C.c_int, [_H, _FP, C.c_int32, C.c_int32, C.c_int32, _FP]),
+    "dr_forward_series_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "dr_set_output_transform": (C.c_int, [_H, _FP, _FP, C.c_float]),
     "dr_s_elems": (C.c_int64, [C.c_int32, C.c_int32]),
     "dr_forward_local_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dr_forward_heads_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

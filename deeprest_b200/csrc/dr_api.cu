@@ -81,6 +81,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
     m->copy_stream = nullptr; m->d_tc_dbg = nullptr;
+    m->x_bstride = 0; m->d_dn = nullptr; m->dn_on = false; m->dn_clamp = 0.0f;
     for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
     for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; }
@@ -116,7 +117,7 @@ void dr_destroy(dr_model* m) {
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
-    void* ptrs[] = {m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+    void* ptrs[] = {m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -334,6 +335,57 @@ int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
     }
     DR_CUDA(m, cudaStreamSynchronize(m->copy_stream));
     DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+// ---- N1: forward straight from the raw series (on-device windowing) ----
+static int series_windows(int32_t N, int32_t W, int32_t stride) {
+    // utils.py:4-5 builds windows for starts i in range(N - W) (it drops the last full window); estimate.py:85-86
+    // then evaluates every `step_size`-th of them.  Starts kept here: 0, stride, 2*stride, ... < N - W.
+    if (N - W <= 0 || stride < 1) return 0;
+    return (N - W - 1) / stride + 1;
+}
+
+int dr_series_windows(int32_t N, int32_t W, int32_t stride) { return series_windows(N, W, stride); }
+
+int dr_forward_series_dev(dr_model* m, const float* series, int32_t N, int32_t W, int32_t stride, float* out) {
+    if (check_handle(m)) return DR_EINVAL;
+    int B = series_windows(N, W, stride);
+    if (!series || !out || B < 1) return dr_fail(m, DR_EINVAL, "dr_forward_series: the series is shorter than one window (the reference's sliding_window returns an empty array)");
+    m->x_bstride = (long long)stride * m->cfg.F;
+    int rc = dr_forward_dev(m, series, B, W, out);
+    m->x_bstride = 0;
+    return rc;
+}
+
+int dr_forward_series(dr_model* m, const float* series, int32_t N, int32_t W, int32_t stride, float* out) {
+    if (check_handle(m)) return DR_EINVAL;
+    int B = series_windows(N, W, stride);
+    if (!series || !out || B < 1) return dr_fail(m, DR_EINVAL, "dr_forward_series: the series is shorter than one window (the reference's sliding_window returns an empty array)");
+    int rc = check_shape(m, B, W);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    size_t nx = (size_t)N * m->cfg.F, no = (size_t)B * W * m->cfg.M * DR_Q;
+    if ((rc = dr_reserve(m, (void**)&m->d_xin, &m->xin_cap, nx * sizeof(float)))) return rc;
+    if ((rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float)))) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(m->d_xin, series, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));   // N*F floats, not B*W*F
+    rc = dr_forward_series_dev(m, m->d_xin, N, W, stride, m->d_out);
+    if (rc != DR_OK) return rc;
+    DR_CUDA(m, cudaMemcpyAsync(out, m->d_out, no * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    return DR_OK;
+}
+
+// ---- N2: clamp + de-normalise fused into the head kernel's epilogue ----
+int dr_set_output_transform(dr_model* m, const float* scale, const float* offset, float clamp_min) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!scale || !offset) { m->dn_on = false; return DR_OK; }
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    if (!m->d_dn) DR_CUDA(m, cudaMalloc((void**)&m->d_dn, (size_t)2 * (m->M_loc ? m->M_loc : 1) * sizeof(float)));
+    DR_CUDA(m, cudaMemcpyAsync(m->d_dn, scale + m->e_lo, m->M_loc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    DR_CUDA(m, cudaMemcpyAsync(m->d_dn + m->M_loc, offset + m->e_lo, m->M_loc * sizeof(float), cudaMemcpyHostToDevice, m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    m->dn_on = true; m->dn_clamp = clamp_min;
     return DR_OK;
 }
 

@@ -76,6 +76,8 @@ struct dr_model {
 
     cudaStream_t stream;
     cudaStream_t own_stream;
+    long long x_bstride;            // 0 = dense windows [B,T,F]; else floats between window starts (series mode, N1)
+    float* d_dn; bool dn_on; float dn_clamp;   // optional output transform: scale[M_loc] | offset[M_loc] (N2)
     unsigned long long* d_tc_dbg;   // optional cycle breakdown of the tcgen05 kernel (dr_debug_read "tc_timing")
     cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
     cudaEvent_t ev_pipe[5];

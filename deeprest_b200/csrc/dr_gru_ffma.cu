@@ -227,14 +227,14 @@ dr_gru_ffma_kernel(const float* __restrict__ xT,     // [T][Fp][Bp]
 
 // x [B,T,F] -> xT [T][Fp][Bp], zero padded in F and B
 __global__ void dr_xT_kernel(const float* __restrict__ x, float* __restrict__ xT,
-                             int B, int T, int F, int Fp, int Bp) {
+                             int B, int T, int F, int Fp, int Bp, long long xbs /* floats between window starts */) {
     __shared__ float tile[32][33];
     // grid: (ceil(Bp/32), ceil(Fp/32), T)
     int t = blockIdx.z;
     int bb = blockIdx.x * 32, ff = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int b = bb + i, f = ff + threadIdx.x;
-        tile[i][threadIdx.x] = (b < B && f < F) ? x[((size_t)b * T + t) * F + f] : 0.0f;
+        tile[i][threadIdx.x] = (b < B && f < F) ? x[(size_t)b * xbs + (size_t)t * F + f] : 0.0f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -265,7 +265,8 @@ int dr_ffma_rows_per_thread(int B) { return B > 64 ? 8 : B > 32 ? 4 : B > 16 ? 2
 
 int dr_launch_xT(dr_model* m, const float* x_dev, int B, int T, int Bp) {
     dim3 grid((Bp + 31) / 32, (m->Fp + 31) / 32, T), block(32, 8);
-    dr_xT_kernel<<<grid, block, 0, m->stream>>>(x_dev, m->d_xT, B, T, m->cfg.F, m->Fp, Bp);
+    dr_xT_kernel<<<grid, block, 0, m->stream>>>(x_dev, m->d_xT, B, T, m->cfg.F, m->Fp, Bp,
+                                                m->x_bstride ? m->x_bstride : (long long)T * m->cfg.F);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;

@@ -468,7 +468,7 @@ __global__ void dr_tc_pack_w_kernel(const float* __restrict__ blob, DrBlobOffset
 
 // x [B,T,F] fp32 -> xtc [T][ntiles][2][hi|lo][128 rows x 64 K] swizzled bf16 images; zero padded
 __global__ void dr_tc_pack_x_kernel(const float* __restrict__ x, uint8_t* __restrict__ xtc,
-                                    int B, int T, int F, int ntiles) {
+                                    int B, int T, int F, int ntiles, long long xbs /* floats between window starts */) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)T * ntiles * 256 * 8;
     if (i >= total) return;
@@ -480,7 +480,7 @@ __global__ void dr_tc_pack_x_kernel(const float* __restrict__ x, uint8_t* __rest
     float v[8];
     for (int j = 0; j < 8; ++j) {
         int f = chunk * 8 + j;
-        v[j] = (b < B && f < F) ? x[((size_t)b * T + t) * F + f] : 0.0f;
+        v[j] = (b < B && f < F) ? x[(size_t)b * xbs + (size_t)t * F + f] : 0.0f;
     }
     uint32_t hi[4], lo[4];
     for (int j = 0; j < 4; ++j) {
@@ -530,7 +530,8 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
     {
         size_t total = (size_t)T * ntiles * 256 * 8;
         unsigned blocks = (unsigned)((total + 255) / 256);
-        dr_tc_pack_x_kernel<<<blocks, 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), B, T, m->cfg.F, ntiles);
+        dr_tc_pack_x_kernel<<<blocks, 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), B, T, m->cfg.F, ntiles,
+                                                           m->x_bstride ? m->x_bstride : (long long)T * m->cfg.F);
         DR_CUDA(m, cudaGetLastError());
     }
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));

@@ -13,7 +13,8 @@ constexpr int TM = 64, TN = 64, TK = 32, LD = 68;
 // ([T][64][Bp][4]) is read as contiguous 1 KB runs.
 __global__ void __launch_bounds__(256)
 dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, const float* __restrict__ hb,
-               float* __restrict__ out, int B, int T, int BpS, int N) {
+               float* __restrict__ out, int B, int T, int BpS, int N,
+               const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
     __shared__ __align__(16) float As[TK][LD];
     __shared__ __align__(16) float Bs[TK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -57,7 +58,14 @@ dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, cons
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             int col = c0 + tx * 4 + j;
-            if (col < N) orow[col] += acc[i][j] + hb[col];
+            if (col < N) {
+                float v = orow[col] + acc[i][j] + hb[col];
+                if (dn_scale) {       // estimate.py:96,102 — clamp the normalised forecast, then undo the min-max scaling
+                    int e = col / DR_Q;
+                    v = fmaxf(v, clamp_min) * dn_scale[e] + dn_offset[e];
+                }
+                orow[col] = v;
+            }
         }
     }
 }
@@ -102,7 +110,8 @@ int dr_launch_heads(dr_model* m, const float* S, int B, int T, float* out_local)
     int N = m->M_loc * DR_Q;
     if (N == 0) return DR_OK;
     dim3 grid((B + TM - 1) / TM, T, (N + TN - 1) / TN);
-    dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, B, T, dr_s_rows(B), N);
+    dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, B, T, dr_s_rows(B), N,
+                                                m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;

@@ -191,6 +191,37 @@ class QuantileRNN:
                                s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
                                interleave_fn=interleave_fn, group=self._pg)
 
+    # ---- steps either side of the path ----------------------------------------
+    def forward_series(self, series, window_size, stride=1):
+        """Forecast straight from the raw traffic series [N,F]: windows series[k*stride : k*stride+window_size]
+        are formed on the device (utils.py:4-5 semantics incl. the dropped last window; estimate.py:85-86 uses
+        stride = step_size).  Returns [n_windows, window_size, M, Q]."""
+        s = np.ascontiguousarray(series.detach().cpu().numpy() if _is_torch(series) else series, np.float32)
+        if s.ndim != 2 or s.shape[1] != self.input_size:
+            raise ValueError(f"series must be [N,{self.input_size}]")
+        n = self._lib.dr_series_windows(s.shape[0], window_size, stride)
+        if n < 1:
+            return np.empty((0, window_size, self.num_metrics, layout.Q), np.float32)
+        out = np.empty((n, window_size, self.num_metrics, layout.Q), np.float32)
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_forward_series(self._h, s.ctypes.data_as(fp), s.shape[0], window_size, stride,
+                                                        out.ctypes.data_as(fp)))
+        return out
+
+    def set_denormalization(self, scales=None, clamp=1e-6):
+        """Fuse estimate.py:96,101-102 into the head kernel: out = max(out, clamp) * range_m + min_m.
+        ``scales`` = [(max-min, min), ...] per metric, exactly the list estimate.py:44-47 builds; None disables."""
+        if scales is None:
+            _lib.check(self._h, self._lib.dr_set_output_transform(self._h, None, None, 0.0))
+            return self
+        sc = np.ascontiguousarray([float(a) for a, _ in scales], np.float32)
+        of = np.ascontiguousarray([float(b) for _, b in scales], np.float32)
+        if sc.size != self.num_metrics:
+            raise ValueError("one (range, min) pair per metric")
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_set_output_transform(self._h, sc.ctypes.data_as(fp), of.ctypes.data_as(fp), float(clamp)))
+        return self
+
     # ---- training ----------------------------------------------------------------------
     def train_step(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0):
         """One iteration of the reference training loop (estimate.py:67-74): train-mode forward

@@ -89,6 +89,21 @@ int  dr_get_weights (dr_model* m, float* host_blob, size_t n_floats);
 int  dr_forward    (dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host);
 int  dr_forward_dev(dr_model* m, const float* x_dev,  int32_t B, int32_t T, float* out_dev);
 
+/* ---- forward straight from the raw traffic series (on-device windowing) ----
+ * Replaces sliding_window (utils.py:4-5) + the strided evaluation loop (estimate.py:85-91): window k is
+ * series[k*stride : k*stride + W], for starts 0, stride, ... < N - W (like the reference, the last full window
+ * is dropped).  series [N,F] -> out [dr_series_windows(N,W,stride), W, M, Q].  The W-fold blow-up of the
+ * windowed tensor never exists: the operand packers read the series with a window stride. */
+int  dr_series_windows(int32_t N, int32_t W, int32_t stride);
+int  dr_forward_series    (dr_model* m, const float* series_host, int32_t N, int32_t W, int32_t stride, float* out_host);
+int  dr_forward_series_dev(dr_model* m, const float* series_dev,  int32_t N, int32_t W, int32_t stride, float* out_dev);
+
+/* ---- optional output transform fused into the head kernel ----
+ * out = max(out, clamp_min) * scale[m] + offset[m]   — estimate.py:96 (clamp on the normalised forecast) and
+ * estimate.py:101-102 (undo normalization_minmax: scale = max-min, offset = min).  scale/offset: host [M].
+ * Pass NULLs to switch it off (the default). */
+int  dr_set_output_transform(dr_model* m, const float* scale_host, const float* offset_host, float clamp_min);
+
 /* ---- expert-sharded forward, device pointers, async ----
  *   1. dr_forward_local_dev : local bi-GRUs.  Writes S_dev = sum over LOCAL experts of their GRU
  *      outputs (dr_s_elems(B,T) floats, stored k-group major [T][2H/4][round_up(B,128)][4]; the

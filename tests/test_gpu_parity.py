@@ -171,3 +171,43 @@ def test_engines_agree_at_config2_shape_sample():
     b = run(M, F, blob, x, "tcgen05")
     assert_parity(b, a, what="tcgen05 vs ffma engine")
     print(f"engines: MAE {np.abs(a - b).mean():.3e} max {np.abs(a - b).max():.3e}")
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_forward_from_raw_series_matches_windowed_forward(engine):
+    """N1: on-device windowing == sliding_window (utils.py:4-5, last window dropped) + forward."""
+    M, F, W = 3, 12, 20
+    blob = synth.weights(17, M, F, 1.5)
+    series = synth.uniform(99, 150 * F).reshape(150, F)
+    m = make_model(M, F, blob, engine)
+    try:
+        for stride in (1, 7, 20):
+            win = oracle.sliding_window(series, W)[::stride]            # estimate.py:85-86 keeps every stride-th window
+            ref = oracle.forward(blob, win, M, F)
+            out = m.forward_series(series, W, stride)
+            assert out.shape == ref.shape
+            assert_parity(out, ref, what=f"series stride {stride}")
+        assert m.forward_series(series[:W], W).shape[0] == 0             # N - W == 0: no window, like the reference
+    finally:
+        m.close()
+
+
+def test_fused_clamp_and_denormalisation():
+    """N2: estimate.py:96 (clamp at 1e-6 on normalised outputs) + :101-102 (x*range + min) in the head epilogue."""
+    M, B, T, F = 4, 6, 9, 8
+    blob = synth.weights(23, M, F, 2.0)
+    x = synth.windows(5, B, T, F, "diurnal")
+    scales = [(3.5, 0.25), (120.0, 7.0), (1.0, 0.0), (0.01, -2.0)]
+    m = make_model(M, F, blob, "tcgen05")
+    try:
+        plain = m(x)
+        m.set_denormalization(scales)
+        fused = m(x)
+        m.set_denormalization(None)
+        again = m(x)
+    finally:
+        m.close()
+    ref = np.maximum(plain, 1e-6) * np.array([a for a, _ in scales], np.float32)[None, None, :, None] \
+        + np.array([b for _, b in scales], np.float32)[None, None, :, None]
+    assert np.abs(fused - ref).max() <= 1e-5 * np.abs(ref).max()
+    assert np.abs(again - plain).max() < 1e-6
