@@ -84,7 +84,8 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->x_bstride = 0; m->d_dn = nullptr; m->dn_on = false; m->dn_clamp = 0.0f;
     for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
-    for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; }
+    for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; }
+    m->d_p = nullptr; m->p_cap = 0; m->p_live = false;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
     m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
 
@@ -118,7 +119,7 @@ void dr_destroy(dr_model* m) {
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
     void* ptrs[] = {m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
-                    m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
+                    m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
@@ -217,6 +218,7 @@ static int forward_local_slot(dr_model* m, const float* x, int32_t B, int32_t T,
     if (use_tc) {
         if (!dr_tc_supported(m, B, T)) return dr_fail(m, DR_EUNSUPPORTED, "tcgen05 engine does not support this shape");
         m->last_engine = "tcgen05";
+        m->p_live = true;          // dr_forward_heads_dev (called next for this chunk) reads the partials from d_p
         return dr_launch_gru_tc(m, x, B, T, S, out_local);     // records its own profile events
     }
     int BT = 16 * dr_ffma_rows_per_thread(B);
@@ -226,6 +228,8 @@ static int forward_local_slot(dr_model* m, const float* x, int32_t B, int32_t T,
     rc = dr_launch_xT(m, x, B, T, Bp);
     if (rc != DR_OK) return rc;
     m->last_engine = "ffma";
+    m->p_live = false;           // this engine REDs its own-expert head term straight into out_local
+    DR_CUDA(m, cudaMemsetAsync(out_local, 0, (size_t)B * T * m->M_loc * DR_Q * sizeof(float), m->stream));
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
     rc = dr_launch_gru_ffma(m, B, T, Bp, S, out_local);
@@ -239,18 +243,18 @@ int dr_forward_local_dev(dr_model* m, const float* x, int32_t B, int32_t T, floa
     if (rc != DR_OK) return rc;
     if (!x || !S || !out_local) return dr_fail(m, DR_EINVAL, "null device pointer");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
-    size_t R = (size_t)B * T;
     DR_CUDA(m, cudaMemsetAsync(S, 0, dr_s_floats(B, T) * sizeof(float), m->stream));
-    DR_CUDA(m, cudaMemsetAsync(out_local, 0, R * m->M_loc * DR_Q * sizeof(float), m->stream));
     if (m->M_loc == 0) return DR_OK;
 
     const int slot = m->ws_slot;
     m->ws_slot = (slot + 1) % 4;
     m->d_xT = m->ws_xT[slot]; m->xT_cap = m->ws_xT_cap[slot];
     m->d_xtc = m->ws_xtc[slot]; m->xtc_cap = m->ws_xtc_cap[slot];
+    m->d_p = m->ws_p[slot]; m->p_cap = m->ws_p_cap[slot];
     rc = forward_local_slot(m, x, B, T, S, out_local);
     m->ws_xT[slot] = m->d_xT; m->ws_xT_cap[slot] = m->xT_cap;
     m->ws_xtc[slot] = m->d_xtc; m->ws_xtc_cap[slot] = m->xtc_cap;
+    m->ws_p[slot] = m->d_p; m->ws_p_cap[slot] = m->p_cap;
     return rc;
 }
 

@@ -66,6 +66,8 @@ struct dr_model {
     // DR_WS_SLOTS forwards may be in flight on different streams (the chunked multi-GPU pipeline); d_xT / d_xtc
     // point at the slot of the call being issued
     float* ws_xT[4]; size_t ws_xT_cap[4]; void* ws_xtc[4]; size_t ws_xtc_cap[4]; int ws_slot;
+    float* ws_p[4]; size_t ws_p_cap[4];
+    float* d_p; size_t p_cap; bool p_live;   // own-expert head partials of the call being issued / consumed (tcgen05 engine)
     float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
     void*  d_xtc;  size_t xtc_cap;  // x split to bf16 hi/lo [T, Bp, Fp]      (tcgen05 engine)
     float* d_S;    size_t S_cap;    // [T][2H/4][Bp][4]

@@ -14,7 +14,8 @@ constexpr int TM = 64, TN = 64, TK = 32, LD = 68;
 __global__ void __launch_bounds__(256)
 dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, const float* __restrict__ hb,
                float* __restrict__ out, int B, int T, int BpS, int N,
-               const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
+               const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min,
+               const float* __restrict__ P /* nullable: own-expert partials [M_loc][2][2][T][Q][BpS] (tcgen05 engine) */) {
     __shared__ __align__(16) float As[TK][LD];
     __shared__ __align__(16) float Bs[TK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -59,7 +60,16 @@ dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, cons
         for (int j = 0; j < 4; ++j) {
             int col = c0 + tx * 4 + j;
             if (col < N) {
-                float v = orow[col] + acc[i][j] + hb[col];
+                float own;
+                if (P) {              // sum the 2 directions x 2 hidden halves the recurrence kernel stored
+                    const int e = col / DR_Q, q = col % DR_Q;
+                    const float* pp = P + (((size_t)e * 4 * T + t) * DR_Q + q) * BpS + b;
+                    const size_t dh = (size_t)T * DR_Q * BpS;
+                    own = (pp[0] + pp[dh]) + (pp[2 * dh] + pp[3 * dh]);
+                } else {
+                    own = orow[col];  // FFMA engine: REDs already accumulated it in place
+                }
+                float v = own + acc[i][j] + hb[col];
                 if (dn_scale) {       // estimate.py:96,102 — clamp the normalised forecast, then undo the min-max scaling
                     int e = col / DR_Q;
                     v = fmaxf(v, clamp_min) * dn_scale[e] + dn_offset[e];
@@ -111,7 +121,8 @@ int dr_launch_heads(dr_model* m, const float* S, int B, int T, float* out_local)
     if (N == 0) return DR_OK;
     dim3 grid((B + TM - 1) / TM, T, (N + TN - 1) / TN);
     dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, B, T, dr_s_rows(B), N,
-                                                m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
+                                                m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp,
+                                                m->p_live ? m->d_p : nullptr);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;
