@@ -85,7 +85,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
     for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; }
-    m->d_p = nullptr; m->p_cap = 0; m->p_live = false;
+    m->d_p = nullptr; m->p_cap = 0; m->p_live = false; m->d_himg = nullptr;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
     m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
 
@@ -118,7 +118,7 @@ void dr_destroy(dr_model* m) {
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
-    void* ptrs[] = {m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+    void* ptrs[] = {m->d_himg, m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -266,7 +266,7 @@ int dr_forward_heads_dev(dr_model* m, const float* S, int32_t B, int32_t T, floa
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[2], m->stream));
-    rc = dr_launch_heads(m, S, B, T, out_local);
+    rc = m->p_live ? dr_launch_heads_tc(m, S, B, T, out_local) : dr_launch_heads(m, S, B, T, out_local);
     if (ev) { DR_CUDA(m, cudaEventRecord(ev[3], m->stream)); m->prof_n += 1; }
     return rc;
 }

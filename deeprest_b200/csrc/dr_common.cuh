@@ -67,6 +67,7 @@ struct dr_model {
     // point at the slot of the call being issued
     float* ws_xT[4]; size_t ws_xT_cap[4]; void* ws_xtc[4]; size_t ws_xtc_cap[4]; int ws_slot;
     float* ws_p[4]; size_t ws_p_cap[4];
+    uint8_t* d_himg;                // K2 weight images for the tcgen05 head GEMM (dr_head_tc.cu)
     float* d_p; size_t p_cap; bool p_live;   // own-expert head partials of the call being issued / consumed (tcgen05 engine)
     float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
     void*  d_xtc;  size_t xtc_cap;  // x split to bf16 hi/lo [T, Bp, Fp]      (tcgen05 engine)
@@ -129,6 +130,9 @@ int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);
 void dr_train_free(dr_model* m);
+// dr_head_tc.cu
+int dr_head_tc_prep(dr_model* m);
+int dr_launch_heads_tc(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 // dr_head.cu
 int dr_launch_heads(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 int dr_launch_interleave(dr_model* m, const float* gathered, int B, int T, float* out);

@@ -513,6 +513,10 @@ bool dr_tc_supported(const dr_model* m, int B, int T) {
 
 int dr_tc_prep_weights(dr_model* m) {
     if (m->cfg.F > 64 || m->M_loc == 0) return DR_OK;
+    {
+        int rc0 = dr_head_tc_prep(m);
+        if (rc0 != DR_OK) return rc0;
+    }
     size_t bytes = (size_t)m->M_loc * 2 * 2 * kWBytes;
     if (!m->d_wtc) {
         DR_CUDA(m, cudaMalloc((void**)&m->d_wtc, bytes));

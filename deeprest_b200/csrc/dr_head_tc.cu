@@ -1,0 +1,247 @@
+// K2 on the tensor cores — the cross-expert-mean head term as a split-fp16 tcgen05 GEMM.
+//
+//   out[b,t,i*Q+q] = own[b,t,i,q]  (4 partials the recurrence kernel stored in P)
+//                  + sum_k S[b,t,k] * (A_i/(M-1))[q,k] + b_i[q]            (qrnn.py:46-54 folded)
+//                  -> optional clamp + de-normalise (estimate.py:96,101-102)
+//
+// GEMM [B*T x 256] x [256 x 3*M_loc].  One CTA = 128 windows of one time step (cta_group::1, M = 128):
+//   * the S tile is read once in its k-group-major layout (coalesced), split to fp16 hi/lo and written as SW128
+//     K-major operand images by the 4 epilogue warps (generic stores + fence.proxy.async), one K-half (128) at a time;
+//   * the weight tile images (96 columns = 32 experts per chunk, pre-split and pre-swizzled by K0) stream in by
+//     1-D bulk copies, double buffered;
+//   * accumulators for up to 384 columns live in TMEM while both K-halves and the 3 split terms accumulate;
+//   * epilogue: tcgen05.ld, add the own-expert partials (coalesced over windows) and the bias, write 64-byte runs.
+// The kernel is memory bound (P 1.8 GB + out 0.45 GB + S 0.3 GB at config 2); the FFMA version it replaces was
+// FFMA bound at 2.2-3.3 ms.
+#include "dr_common.cuh"
+#include "dr_tc.cuh"
+
+using namespace drtc;
+
+namespace {
+
+constexpr int kHThreads = 192;                      // warps 0-3: convert + epilogue, 4: MMA issuer, 5: weight producer
+constexpr int kNC = 96;                             // columns per chunk (32 experts x Q)
+constexpr int kGroupChunks = 4;                     // 384 accumulator columns per pass
+constexpr uint32_t kABlk = 128 * 128;               // A block: 128 rows x 64 K fp16
+constexpr uint32_t kAHalf = 4 * kABlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one K-half)
+constexpr uint32_t kBBlk = kNC * 128;               // B block: 96 rows x 64 K fp16
+constexpr uint32_t kBTile = 4 * kBBlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one chunk, one K-half)
+constexpr uint32_t kHOffA = 0, kHOffB = kAHalf, kHOffBar = kHOffB + 2 * kBTile;
+constexpr uint32_t kHSmem = kHOffBar + 128;
+
+enum HBar { A_READY = 0, A_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, D_FULL, D_FREE, H_NUM };
+
+__global__ void __launch_bounds__(kHThreads, 1)
+dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
+                  const uint8_t* __restrict__ wimg,   // [n_chunks][2 khalf][kBTile]
+                  const float* __restrict__ hb,       // [M_loc*Q]
+                  const float* __restrict__ P,        // [M_loc][4][T][Q][Bp]
+                  float* __restrict__ out,            // [B][T][N]
+                  int B, int T, int Bp, int N, int n_chunks,
+                  const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b0 = blockIdx.x * 128, t = blockIdx.y;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kHOffBar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + H_NUM);
+    auto bar = [&](int i) { return smem_u32(&bars[i]); };
+
+    if (tid == 0) {
+        mbar_init(bar(A_READY), 128); mbar_init(bar(A_FREE), 1);
+        mbar_init(bar(B_FULL0), 1); mbar_init(bar(B_FULL1), 1);
+        mbar_init(bar(B_EMPTY0), 1); mbar_init(bar(B_EMPTY1), 1);
+        mbar_init(bar(D_FULL), 1); mbar_init(bar(D_FREE), 128);
+        fence_mbar_init();
+    }
+    if (warp == 4) { tmem_alloc<1>(smem_u32(tmem_slot), 512); tmem_relinquish<1>(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+    const int n_groups = (n_chunks + kGroupChunks - 1) / kGroupChunks;
+
+    if (warp < 4) {
+        // ===================== S converter + epilogue (thread == window row) =====================
+        const int row = tid, b = b0 + row;
+        const bool live = b < B;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        uint32_t a_free_uses = 0;
+        for (int g = 0; g < n_groups; ++g) {
+            for (int kh = 0; kh < 2; ++kh) {
+                if (g > 0 || kh > 0) { mbar_wait(bar(A_FREE), a_free_uses & 1); ++a_free_uses; }   // MMAs done reading the A image
+                // 32 k-groups of this K-half: float4 (4 consecutive k) per k-group, coalesced over rows
+#pragma unroll 4
+                for (int kg2 = 0; kg2 < 16; ++kg2) {          // two k-groups -> one 16-byte fp16 chunk (8 k)
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (live) {
+                        const float* sp = S + (((size_t)t * 64 + kh * 32 + kg2 * 2) * Bp + b) * 4;
+                        v0 = *reinterpret_cast<const float4*>(sp);
+                        v1 = *reinterpret_cast<const float4*>(sp + (size_t)Bp * 4);
+                    }
+                    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        __half h0, l0, h1, l1;
+                        split_f16(vv[2 * j], h0, l0); split_f16(vv[2 * j + 1], h1, l1);
+                        hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+                    }
+                    const int kb = kg2 >> 3;                   // 64-wide K block inside the half
+                    const uint32_t o = sw128_offset(row, (kg2 & 7) * 8);
+                    *reinterpret_cast<uint4*>(smem + kHOffA + kb * kABlk + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(smem + kHOffA + (2 + kb) * kABlk + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                fence_proxy_async();                           // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(bar(A_READY));
+            }
+            // ---- epilogue of this column group ----
+            mbar_wait(bar(D_FULL), g & 1);
+            tc_fence_after();
+            const int c_lo = g * kGroupChunks * kNC;
+            const int c_hi = min(N, c_lo + kGroupChunks * kNC);
+            for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(tbase + lane_base + (uint32_t)(c0 - c_lo), v);
+                tc_wait_ld();
+                if (live) {
+                    float r[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = c0 + j;
+                        float val = 0.0f;
+                        if (col < N) {
+                            const int e = col / DR_Q, q = col - e * DR_Q;
+                            const float* pp = P + (((size_t)e * 4 * T + t) * DR_Q + q) * Bp + b;
+                            const size_t dh = (size_t)T * DR_Q * Bp;
+                            const float own = (pp[0] + pp[dh]) + (pp[2 * dh] + pp[3 * dh]);
+                            val = own + __uint_as_float(v[j]) + hb[col];
+                            if (dn_scale) val = fmaxf(val, clamp_min) * dn_scale[e] + dn_offset[e];
+                        }
+                        r[j] = val;
+                    }
+                    float* o = out + ((size_t)b * T + t) * N + c0;
+                    if (c0 + 16 <= N && (N & 3) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    } else {
+                        for (int j = 0; j < 16 && c0 + j < N; ++j) o[j] = r[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar(D_FREE));                          // accumulators may be overwritten by the next group
+        }
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_f16(128, kNC);
+            const uint64_t adesc = make_desc_sw128(smem_u32(smem + kHOffA));
+            uint32_t a_ready_uses = 0, bfull_uses[2] = {0, 0};
+            for (int g = 0; g < n_groups; ++g) {
+                if (g > 0) { mbar_wait(bar(D_FREE), (g - 1) & 1); tc_fence_after(); }
+                const int cg0 = g * kGroupChunks, cg1 = min(n_chunks, cg0 + kGroupChunks);
+                for (int kh = 0; kh < 2; ++kh) {
+                    mbar_wait(bar(A_READY), a_ready_uses & 1); ++a_ready_uses;
+                    tc_fence_after();
+                    for (int c = cg0; c < cg1; ++c) {
+                        const int buf = (int)((bfull_uses[0] + bfull_uses[1]) & 1);
+                        mbar_wait(bar(B_FULL0 + buf), bfull_uses[buf] & 1); ++bfull_uses[buf];
+                        tc_fence_after();
+                        const uint64_t bdesc = make_desc_sw128(smem_u32(smem + kHOffB + buf * kBTile));
+                        const uint32_t d = tbase + (uint32_t)((c - cg0) * kNC);
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t ao = (term == 2) ? 2 * kABlk : 0;        // A: hi, hi, lo
+                            const uint32_t bo = (term == 1) ? 2 * kBBlk : 0;        // B: hi, lo, hi
+#pragma unroll
+                            for (int ks = 0; ks < 8; ++ks) {
+                                const int kb = ks >> 2, k16 = ks & 3;
+                                mma_ss<1>(d, adesc + ((ao + kb * kABlk + k16 * 32) >> 4), bdesc + ((bo + kb * kBBlk + k16 * 32) >> 4),
+                                          idesc, (kh | term | ks) ? 1u : 0u);
+                            }
+                        }
+                        mma_commit_1(bar(B_EMPTY0 + buf));
+                    }
+                    mma_commit_1(bar(A_FREE));
+                }
+                mma_commit_1(bar(D_FULL));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== weight-image producer =====================
+        if (elect_one()) {
+            uint32_t n = 0;
+            for (int g = 0; g < n_groups; ++g) {
+                const int cg0 = g * kGroupChunks, cg1 = min(n_chunks, cg0 + kGroupChunks);
+                for (int kh = 0; kh < 2; ++kh)
+                    for (int c = cg0; c < cg1; ++c, ++n) {
+                        const int buf = (int)(n & 1);
+                        if (n >= 2) mbar_wait(bar(B_EMPTY0 + buf), ((n >> 1) - 1) & 1);
+                        mbar_expect_tx(bar(B_FULL0 + buf), kBTile);
+                        bulk_g2s(smem_u32(smem + kHOffB + buf * kBTile), wimg + ((size_t)c * 2 + kh) * kBTile, kBTile, bar(B_FULL0 + buf));
+                    }
+            }
+        }
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<1>(tbase, 512);
+}
+
+// weight images: one thread per (chunk, khalf, row 0..95, 16-byte K chunk 0..15)
+__global__ void dr_head_tc_pack_kernel(const float* __restrict__ abar, int N, uint8_t* __restrict__ wimg, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int c8 = (int)(i % 16); size_t r = i / 16;
+    int row = (int)(r % kNC); r /= kNC;
+    int kh = (int)(r % 2); int c = (int)(r / 2);
+    int col = c * kNC + row;
+    uint32_t hi[4], lo[4];
+    for (int j = 0; j < 4; ++j) {
+        float v0 = 0.f, v1 = 0.f;
+        if (col < N) {
+            const float* a = abar + (size_t)col * DR_2H + kh * 128 + c8 * 8 + 2 * j;
+            v0 = a[0]; v1 = a[1];
+        }
+        __half h0, l0, h1, l1;
+        split_f16(v0, h0, l0); split_f16(v1, h1, l1);
+        hi[j] = pack_h2(h0, h1); lo[j] = pack_h2(l0, l1);
+    }
+    int kb = c8 >> 3;
+    uint32_t o = sw128_offset(row, (c8 & 7) * 8);
+    uint8_t* base = wimg + ((size_t)c * 2 + kh) * kBTile;
+    *reinterpret_cast<uint4*>(base + kb * kBBlk + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + (2 + kb) * kBBlk + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+}  // namespace
+
+int dr_head_tc_prep(dr_model* m) {
+    int N = m->M_loc * DR_Q;
+    if (N == 0) return DR_OK;
+    int n_chunks = (N + kNC - 1) / kNC;
+    size_t bytes = (size_t)n_chunks * 2 * kBTile;
+    if (!m->d_himg) DR_CUDA(m, cudaMalloc((void**)&m->d_himg, bytes));
+    size_t total = (size_t)n_chunks * 2 * kNC * 16;
+    dr_head_tc_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(m->d_abar, N, m->d_himg, total);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
+
+int dr_launch_heads_tc(dr_model* m, const float* S, int B, int T, float* out_local) {
+    int N = m->M_loc * DR_Q;
+    if (N == 0) return DR_OK;
+    int n_chunks = (N + kNC - 1) / kNC;
+    DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
+    dim3 grid((B + 127) / 128, T);
+    dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
+        S, m->d_himg, m->d_hb, m->d_p, out_local, B, T, dr_s_rows(B), N, n_chunks,
+        m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
