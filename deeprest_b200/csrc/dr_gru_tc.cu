@@ -75,7 +75,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                  const float* __restrict__ bias4,     // [M_loc][2][4][H]
                  const float* __restrict__ ct,        // [M_loc][2][Q][H]
                  float* __restrict__ S,               // [T][64][Bp][4]
-                 float* __restrict__ P,               // own-expert head partials [M_loc][2 dir][2 half][T][Q][Bp]
+                 float* __restrict__ P,               // own-expert head partials [T][Bp/128][ceil(3M_loc/16)][dir*2+half][16][128]
                  int B, int T, int Bp, int M_loc, int ntiles,
                  unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -199,8 +199,16 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
         // scattered into out[B,T,M,Q], which cost a DRAM read-modify-write per touch.
         auto flush = [&](int ttp) {
             if (live) {
-                float* o = P + ((((size_t)(e * 2 + dir) * 2 + half) * T + ttp) * DR_Q) * Bp + b;
-                o[0] = o0; o[(size_t)Bp] = o1; o[2 * (size_t)Bp] = o2;
+                // P is laid out [t][128-window tile][16-column group][dir*2+half][16][128]: what the head kernel's CTA (t, tile)
+                // needs for 16 output columns is one contiguous 32 KB slab (one bulk copy), and a warp stores 128 contiguous bytes
+                const int ngrp = (M_loc * DR_Q + 15) >> 4;
+                const size_t slab = (((size_t)ttp * (Bp >> 7) + (b >> 7)) * ngrp) * 4 * 16 * 128;
+                const int dh = dir * 2 + half;
+                const int c = e * DR_Q;
+                float* o = P + slab + (b & 127);
+                o[((size_t)((c >> 4) * 4 + dh) * 16 + (c & 15)) * 128] = o0;
+                o[((size_t)(((c + 1) >> 4) * 4 + dh) * 16 + ((c + 1) & 15)) * 128] = o1;
+                o[((size_t)(((c + 2) >> 4) * 4 + dh) * 16 + ((c + 2) & 15)) * 128] = o2;
             }
             o0 = 0.f; o1 = 0.f; o2 = 0.f;
         };
@@ -536,7 +544,7 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
     int ntiles = (B + 255) / 256;
     int Bp = (B + 127) / 128 * 128;
     {
-        int rc0 = dr_reserve(m, (void**)&m->d_p, &m->p_cap, (size_t)m->M_loc * 2 * 2 * T * DR_Q * Bp * sizeof(float));
+        int rc0 = dr_reserve(m, (void**)&m->d_p, &m->p_cap, (size_t)T * (Bp / 128) * ((m->M_loc * DR_Q + 15) / 16) * 4 * 16 * 128 * sizeof(float));
         if (rc0 != DR_OK) return rc0;
     }
     size_t xbytes = (size_t)T * ntiles * 2 * kXStage;

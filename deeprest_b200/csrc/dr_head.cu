@@ -15,7 +15,7 @@ __global__ void __launch_bounds__(256)
 dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, const float* __restrict__ hb,
                float* __restrict__ out, int B, int T, int BpS, int N,
                const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min,
-               const float* __restrict__ P /* nullable: own-expert partials [M_loc][2][2][T][Q][BpS] (tcgen05 engine) */) {
+               const float* __restrict__ P /* nullable: own-expert partials [T][BpS/128][ceil(N/16)][4][16][128] (tcgen05 engine) */) {
     __shared__ __align__(16) float As[TK][LD];
     __shared__ __align__(16) float Bs[TK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -63,9 +63,11 @@ dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, cons
                 float own;
                 if (P) {              // sum the 2 directions x 2 hidden halves the recurrence kernel stored
                     const int e = col / DR_Q, q = col % DR_Q;
-                    const float* pp = P + (((size_t)e * 4 * T + t) * DR_Q + q) * BpS + b;
-                    const size_t dh = (size_t)T * DR_Q * BpS;
+                    const int ngrp = (N + 15) >> 4;
+                    const float* pp = P + (((((size_t)t * (BpS >> 7) + (b >> 7)) * ngrp + (col >> 4)) * 4) * 16 + (col & 15)) * 128 + (b & 127);
+                    const size_t dh = (size_t)16 * 128;
                     own = (pp[0] + pp[dh]) + (pp[2 * dh] + pp[3 * dh]);
+                    (void)e; (void)q;
                 } else {
                     own = orow[col];  // FFMA engine: REDs already accumulated it in place
                 }

@@ -27,16 +27,17 @@ constexpr uint32_t kABlk = 128 * 128;               // A block: 128 rows x 64 K 
 constexpr uint32_t kAHalf = 4 * kABlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one K-half)
 constexpr uint32_t kBBlk = kNC * 128;               // B block: 96 rows x 64 K fp16
 constexpr uint32_t kBTile = 4 * kBBlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one chunk, one K-half)
-constexpr uint32_t kHOffA = 0, kHOffB = kAHalf, kHOffBar = kHOffB + 2 * kBTile;
+constexpr uint32_t kPSlab = 4 * 16 * 128 * 4;       // own-expert partials of 16 columns: [dir*2+half][16][128 rows] fp32 = 32 KB
+constexpr uint32_t kHOffA = 0, kHOffB = kAHalf, kHOffP = kHOffB + 2 * kBTile, kHOffBar = kHOffP + 2 * kPSlab;
 constexpr uint32_t kHSmem = kHOffBar + 128;
 
-enum HBar { A_READY = 0, A_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, D_FULL, D_FREE, H_NUM };
+enum HBar { A_READY = 0, A_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, D_FULL, D_FREE, P_FULL0, P_FULL1, P_EMPTY0, P_EMPTY1, H_NUM };
 
 __global__ void __launch_bounds__(kHThreads, 1)
 dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                   const uint8_t* __restrict__ wimg,   // [n_chunks][2 khalf][kBTile]
                   const float* __restrict__ hb,       // [M_loc*Q]
-                  const float* __restrict__ P,        // [M_loc][4][T][Q][Bp]
+                  const float* __restrict__ P,        // [T][Bp/128][ceil(N/16)][4][16][128]
                   float* __restrict__ out,            // [B][T][N]
                   int B, int T, int Bp, int N, int n_chunks,
                   const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
@@ -52,6 +53,7 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
         mbar_init(bar(B_FULL0), 1); mbar_init(bar(B_FULL1), 1);
         mbar_init(bar(B_EMPTY0), 1); mbar_init(bar(B_EMPTY1), 1);
         mbar_init(bar(D_FULL), 1); mbar_init(bar(D_FREE), 128);
+        mbar_init(bar(P_FULL0), 1); mbar_init(bar(P_FULL1), 1); mbar_init(bar(P_EMPTY0), 128); mbar_init(bar(P_EMPTY1), 128);
         fence_mbar_init();
     }
     if (warp == 4) { tmem_alloc<1>(smem_u32(tmem_slot), 512); tmem_relinquish<1>(); }
@@ -66,7 +68,7 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
         const int row = tid, b = b0 + row;
         const bool live = b < B;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        uint32_t a_free_uses = 0;
+        uint32_t a_free_uses = 0, p_uses = 0;
         for (int g = 0; g < n_groups; ++g) {
             for (int kh = 0; kh < 2; ++kh) {
                 if (g > 0 || kh > 0) { mbar_wait(bar(A_FREE), a_free_uses & 1); ++a_free_uses; }   // MMAs done reading the A image
@@ -104,6 +106,20 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                 uint32_t v[16];
                 tmem_ld16(tbase + lane_base + (uint32_t)(c0 - c_lo), v);
                 tc_wait_ld();
+                // the 16 columns' own-expert partials arrive as one 32 KB slab by bulk copy (producer warp, 2-deep ring): with
+                // 4 resident epilogue warps plain loads could not keep enough bytes in flight (ncu r01: DRAM at 7 %)
+                const uint32_t pbuf = p_uses & 1;
+                mbar_wait(bar(P_FULL0 + pbuf), (p_uses >> 1) & 1);
+                ++p_uses;
+                float pv[4][16];
+                {
+                    const float* ps = reinterpret_cast<const float*>(smem + kHOffP + pbuf * kPSlab) + row;
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pv[d][j] = ps[(d * 16 + j) * 128];
+                }
+                mbar_arrive(bar(P_EMPTY0 + pbuf));
                 if (live) {
                     float r[16];
 #pragma unroll
@@ -111,10 +127,8 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                         const int col = c0 + j;
                         float val = 0.0f;
                         if (col < N) {
-                            const int e = col / DR_Q, q = col - e * DR_Q;
-                            const float* pp = P + (((size_t)e * 4 * T + t) * DR_Q + q) * Bp + b;
-                            const size_t dh = (size_t)T * DR_Q * Bp;
-                            const float own = (pp[0] + pp[dh]) + (pp[2 * dh] + pp[3 * dh]);
+                            const int e = col / DR_Q;
+                            const float own = (pv[0][j] + pv[1][j]) + (pv[2][j] + pv[3][j]);
                             val = own + __uint_as_float(v[j]) + hb[col];
                             if (dn_scale) val = fmaxf(val, clamp_min) * dn_scale[e] + dn_offset[e];
                         }
@@ -172,7 +186,9 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
     } else {
         // ===================== weight-image producer =====================
         if (elect_one()) {
-            uint32_t n = 0;
+            uint32_t n = 0, np = 0;
+            const int ngrp16 = (N + 15) >> 4;
+            const uint8_t* pcta = reinterpret_cast<const uint8_t*>(P) + ((size_t)t * (Bp >> 7) + blockIdx.x) * ngrp16 * kPSlab;
             for (int g = 0; g < n_groups; ++g) {
                 const int cg0 = g * kGroupChunks, cg1 = min(n_chunks, cg0 + kGroupChunks);
                 for (int kh = 0; kh < 2; ++kh)
@@ -182,6 +198,14 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                         mbar_expect_tx(bar(B_FULL0 + buf), kBTile);
                         bulk_g2s(smem_u32(smem + kHOffB + buf * kBTile), wimg + ((size_t)c * 2 + kh) * kBTile, kBTile, bar(B_FULL0 + buf));
                     }
+                // own-expert partial slabs of this column group, in the order the epilogue consumes them
+                const int s_lo = g * kGroupChunks * kNC / 16, s_hi = (min(N, (g + 1) * kGroupChunks * kNC) + 15) / 16;
+                for (int sl = s_lo; sl < s_hi; ++sl, ++np) {
+                    const int buf = (int)(np & 1);
+                    if (np >= 2) mbar_wait(bar(P_EMPTY0 + buf), ((np >> 1) - 1) & 1);
+                    mbar_expect_tx(bar(P_FULL0 + buf), kPSlab);
+                    bulk_g2s(smem_u32(smem + kHOffP + buf * kPSlab), pcta + (size_t)sl * kPSlab, kPSlab, bar(P_FULL0 + buf));
+                }
             }
         }
         __syncwarp();

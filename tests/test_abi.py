@@ -92,3 +92,12 @@ def test_expert_sharding_plan():
         assert spans[0][0] == 0 and spans[-1][1] == M
         for (a, b), (c, d) in zip(spans, spans[1:]):
             assert b == c and a % 2 == 0
+
+
+def test_series_window_count_matches_reference_sliding_window():
+    """dr_series_windows mirrors utils.py:4-5 (range(len - W): the last full window is dropped) + a stride."""
+    from oracle import qrnn_numpy as oracle
+    lib = _lib.load()
+    for N, W, stride in [(150, 20, 1), (150, 20, 7), (150, 20, 20), (20, 20, 1), (21, 20, 1), (3, 60, 1), (100, 60, 60)]:
+        ref = len(oracle.sliding_window(np.zeros((N, 2)), W)[::stride]) if N - W > 0 else 0
+        assert lib.dr_series_windows(N, W, stride) == ref, (N, W, stride)
