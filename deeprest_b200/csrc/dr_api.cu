@@ -80,9 +80,10 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wtc = nullptr; m->wtc_bytes = 0;
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
-    m->copy_stream = nullptr; m->d_tc_dbg = nullptr;
+    m->copy_stream = nullptr; m->stream2 = nullptr; m->d_tc_dbg = nullptr;
+    for (int i = 0; i < 4; ++i) { m->ws_S[i] = nullptr; m->ws_S_cap[i] = 0; }
     m->x_bstride = 0; m->d_dn = nullptr; m->dn_on = false; m->dn_clamp = 0.0f;
-    for (int i = 0; i < 5; ++i) m->ev_pipe[i] = nullptr;
+    for (int i = 0; i < 10; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
     for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; }
     m->d_p = nullptr; m->p_cap = 0; m->p_live = false; m->d_himg = nullptr;
@@ -119,11 +120,12 @@ void dr_destroy(dr_model* m) {
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
     void* ptrs[] = {m->d_himg, m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
-                    m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->d_S, m->d_out, m->d_xin, m->d_loss, m->d_y};
+                    m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->ws_S[0], m->ws_S[1], m->ws_S[2], m->ws_S[3], m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
-    for (int i = 0; i < 5; ++i) if (m->ev_pipe[i]) cudaEventDestroy(m->ev_pipe[i]);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
+    for (int i = 0; i < 10; ++i) if (m->ev_pipe[i]) cudaEventDestroy(m->ev_pipe[i]);
     if (m->ev) { for (int i = 0; i < 4 * DR_PROF_MAX; ++i) if (m->ev[i]) cudaEventDestroy(m->ev[i]); delete[] m->ev; }
     delete m;
 }
@@ -284,7 +286,12 @@ int dr_forward_dev(dr_model* m, const float* x, int32_t B, int32_t T, float* out
         return dr_fail(m, DR_ESTATE, "dr_forward needs world == 1; sharded handles use dr_forward_local_dev / dr_forward_heads_dev");
     int rc = check_shape(m, B, T);
     if (rc != DR_OK) return rc;
+    // S rotates through the same slots as the operand-image workspaces, so chunked callers may keep several
+    // forwards in flight on different streams; d_S is the slot of the latest call (dr_debug_read "S")
+    const int slot = m->ws_slot;
+    m->d_S = m->ws_S[slot]; m->S_cap = m->ws_S_cap[slot];
     rc = dr_reserve(m, (void**)&m->d_S, &m->S_cap, dr_s_floats(B, T) * sizeof(float));
+    m->ws_S[slot] = m->d_S; m->ws_S_cap[slot] = m->S_cap;
     if (rc != DR_OK) return rc;
     rc = dr_forward_local_dev(m, x, B, T, m->d_S, out);     // world == 1: out_local IS out [B,T,M,Q]
     if (rc != DR_OK) return rc;
@@ -302,15 +309,13 @@ int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
     if (rc != DR_OK) return rc;
     rc = dr_reserve(m, (void**)&m->d_out, &m->out_cap, no * sizeof(float));
     if (rc != DR_OK) return rc;
-    // Windows are independent, so a large batch runs as two half-batches: the H2D copy of the second half
-    // and the D2H copy of the first half's forecasts overlap the other half's kernels (copy engine on its
-    // own stream, ordered with events).  Halves are multiples of 256 windows = whole tensor-core pair tiles.
-    int nc = (B >= 512) ? 2 : 1;
-    int Bc = (nc == 2) ? ((B / 2 + 255) / 256) * 256 : B;
-    if (nc == 2 && !m->copy_stream) {
-        DR_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 5; ++i) DR_CUDA(m, cudaEventCreateWithFlags(&m->ev_pipe[i], cudaEventDisableTiming));
-    }
+    // Windows are independent, so a large batch runs as 2-4 chunks of whole 256-window pair tiles: the H2D copy of
+    // the next chunks and the D2H copy of finished forecasts ride the copy engine (own stream, ordered with events)
+    // while other chunks compute; the chunks alternate between two compute streams so that one chunk's recurrence
+    // CTAs fill the SMs the previous chunk's last wave leaves idle.
+    int nc = (B >= 1024) ? 4 : (B >= 512) ? 2 : 1;
+    int Bc = (nc > 1) ? ((B / nc + 255) / 256) * 256 : B;
+    if (nc > 1) nc = (B + Bc - 1) / Bc;
     if (nc == 1) {
         DR_CUDA(m, cudaMemcpyAsync(m->d_xin, x, nx * sizeof(float), cudaMemcpyHostToDevice, m->stream));
         rc = dr_forward_dev(m, m->d_xin, B, T, m->d_out);
@@ -319,10 +324,17 @@ int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
         DR_CUDA(m, cudaStreamSynchronize(m->stream));
         return DR_OK;
     }
+    if (!m->copy_stream) {
+        DR_CUDA(m, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        DR_CUDA(m, cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+        for (int i = 0; i < 10; ++i) DR_CUDA(m, cudaEventCreateWithFlags(&m->ev_pipe[i], cudaEventDisableTiming));
+    }
     const size_t xrow = (size_t)T * m->cfg.F, orow = (size_t)T * m->cfg.M * DR_Q;
-    // the copy stream must not start before earlier work on the compute stream that may still use the staging buffers
-    DR_CUDA(m, cudaEventRecord(m->ev_pipe[4], m->stream));
-    DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[4], 0));
+    cudaStream_t main_stream = m->stream;
+    // nothing may start before earlier work on the caller's stream that still uses the staging buffers
+    DR_CUDA(m, cudaEventRecord(m->ev_pipe[8], main_stream));
+    DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[8], 0));
+    DR_CUDA(m, cudaStreamWaitEvent(m->stream2, m->ev_pipe[8], 0));
     for (int c = 0; c < nc; ++c) {
         int b0 = c * Bc, bn = (c == nc - 1) ? B - b0 : Bc;
         DR_CUDA(m, cudaMemcpyAsync(m->d_xin + b0 * xrow, x + b0 * xrow, bn * xrow * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
@@ -330,15 +342,19 @@ int dr_forward(dr_model* m, const float* x, int32_t B, int32_t T, float* out) {
     }
     for (int c = 0; c < nc; ++c) {
         int b0 = c * Bc, bn = (c == nc - 1) ? B - b0 : Bc;
-        DR_CUDA(m, cudaStreamWaitEvent(m->stream, m->ev_pipe[c], 0));
+        cudaStream_t cs = (c & 1) ? m->stream2 : main_stream;
+        DR_CUDA(m, cudaStreamWaitEvent(cs, m->ev_pipe[c], 0));
+        m->stream = cs;
         rc = dr_forward_dev(m, m->d_xin + b0 * xrow, bn, T, m->d_out + b0 * orow);
+        m->stream = main_stream;
         if (rc != DR_OK) return rc;
-        DR_CUDA(m, cudaEventRecord(m->ev_pipe[2 + c], m->stream));
-        DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[2 + c], 0));
+        DR_CUDA(m, cudaEventRecord(m->ev_pipe[4 + c], cs));
+        DR_CUDA(m, cudaStreamWaitEvent(m->copy_stream, m->ev_pipe[4 + c], 0));
         DR_CUDA(m, cudaMemcpyAsync(out + b0 * orow, m->d_out + b0 * orow, bn * orow * sizeof(float), cudaMemcpyDeviceToHost, m->copy_stream));
     }
     DR_CUDA(m, cudaStreamSynchronize(m->copy_stream));
-    DR_CUDA(m, cudaStreamSynchronize(m->stream));
+    DR_CUDA(m, cudaStreamSynchronize(m->stream2));
+    DR_CUDA(m, cudaStreamSynchronize(main_stream));
     return DR_OK;
 }
 

@@ -83,7 +83,9 @@ struct dr_model {
     float* d_dn; bool dn_on; float dn_clamp;   // optional output transform: scale[M_loc] | offset[M_loc] (N2)
     unsigned long long* d_tc_dbg;   // optional cycle breakdown of the tcgen05 kernel (dr_debug_read "tc_timing")
     cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
-    cudaEvent_t ev_pipe[5];
+    cudaStream_t stream2;           // second compute stream of the pipelined host entry point
+    cudaEvent_t ev_pipe[10];
+    float* ws_S[4]; size_t ws_S_cap[4];
     int64_t launches;
     bool profile;
     int prof_n;                     // forwards recorded since dr_profile(m,1)
