@@ -59,6 +59,7 @@ def test_forward_matches_reference_golden(path, engine):
     (5, 70, 12, 20, 1.5),     # FFMA 128-row tile with padding rows; F not multiple of 16
     (4, 129, 6, 64, 1.0),     # crosses a 128-row tile
     (2, 256, 4, 100, 1.0),    # F > 64
+    (130, 3, 4, 6, 1.0),      # many experts: 390 head columns = two TMEM column groups, last chunk partial
 ])
 def test_forward_matches_oracle(M, B, T, F, scale, engine):
     blob = synth.weights(100 + M + F, M, F, scale)
