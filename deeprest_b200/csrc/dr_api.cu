@@ -273,6 +273,21 @@ int dr_forward_heads_dev(dr_model* m, const float* S, int32_t B, int32_t T, floa
     return rc;
 }
 
+int dr_forward_heads_p2p_dev(dr_model* m, const float* S, int32_t B, int32_t T, void* const* out_ptrs, int32_t n_ptrs,
+                             int64_t row0) {
+    if (check_handle(m)) return DR_EINVAL;
+    int rc = check_shape(m, B, T);
+    if (rc != DR_OK) return rc;
+    if (!S || !out_ptrs || n_ptrs != m->cfg.world) return dr_fail(m, DR_EINVAL, "dr_forward_heads_p2p_dev: one destination per rank");
+    if (!m->p_live) return dr_fail(m, DR_EUNSUPPORTED, "peer-write heads need the tcgen05 engine (input_size <= 64)");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    cudaEvent_t* ev = dr_prof_slot(m);
+    if (ev) DR_CUDA(m, cudaEventRecord(ev[2], m->stream));
+    rc = dr_launch_heads_tc_dst(m, S, B, T, out_ptrs, n_ptrs, row0);
+    if (ev) { DR_CUDA(m, cudaEventRecord(ev[3], m->stream)); m->prof_n += 1; }
+    return rc;
+}
+
 int dr_interleave_dev(dr_model* m, const float* gathered, int32_t B, int32_t T, float* out) {
     if (check_handle(m)) return DR_EINVAL;
     if (!gathered || !out || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "bad argument");

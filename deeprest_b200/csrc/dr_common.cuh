@@ -135,6 +135,7 @@ void dr_train_free(dr_model* m);
 // dr_head_tc.cu
 int dr_head_tc_prep(dr_model* m);
 int dr_launch_heads_tc(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
+int dr_launch_heads_tc_dst(dr_model* m, const float* S_dev, int B, int T, void* const* dst_ptrs, int n_dst, long long row0);
 // dr_head.cu
 int dr_launch_heads(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 int dr_launch_interleave(dr_model* m, const float* gathered, int B, int T, float* out);

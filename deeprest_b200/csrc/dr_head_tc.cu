@@ -31,6 +31,17 @@ constexpr uint32_t kPSlab = 4 * 16 * 128 * 4;       // own-expert partials of 16
 constexpr uint32_t kHOffA = 0, kHOffB = kAHalf, kHOffP = kHOffB + 2 * kBTile, kHOffBar = kHOffP + 2 * kPSlab;
 constexpr uint32_t kHSmem = kHOffBar + 128;
 
+// Destinations of the forecasts. world == 1: the caller's out [B,T,N].  Expert-sharded: every rank's full forecast tensor
+// [Bfull,T,world*N] (peer-mapped symmetric memory) — this rank's N columns are stored into ALL of them straight from the
+// epilogue, over NVLink for the peers: the all-gather of the forecasts and the layout interleave are fused into K2.
+struct HeadDst {
+    float* ptr[8];
+    int world;          // number of destinations
+    int ld;             // row length of a destination (world*N, or N)
+    int col0;           // this rank's first column (rank*N, or 0)
+    long long row0;     // first window of this call inside the destination (chunked callers)
+};
+
 enum HBar { A_READY = 0, A_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, D_FULL, D_FREE, P_FULL0, P_FULL1, P_EMPTY0, P_EMPTY1, H_NUM };
 
 __global__ void __launch_bounds__(kHThreads, 1)
@@ -38,7 +49,7 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                   const uint8_t* __restrict__ wimg,   // [n_chunks][2 khalf][kBTile]
                   const float* __restrict__ hb,       // [M_loc*Q]
                   const float* __restrict__ P,        // [T][Bp/128][ceil(N/16)][4][16][128]
-                  float* __restrict__ out,            // [B][T][N]
+                  HeadDst dst,
                   int B, int T, int Bp, int N, int n_chunks,
                   const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -134,12 +145,16 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                         }
                         r[j] = val;
                     }
-                    float* o = out + ((size_t)b * T + t) * N + c0;
-                    if (c0 + 16 <= N && (N & 3) == 0) {
+                    const size_t off = ((size_t)(dst.row0 + b) * T + t) * dst.ld + dst.col0 + c0;
+                    const bool vec = (c0 + 16 <= N) && ((dst.ld | dst.col0) & 3) == 0;
+                    for (int w = 0; w < dst.world; ++w) {
+                        float* o = dst.ptr[w] + off;
+                        if (vec) {
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                    } else {
-                        for (int j = 0; j < 16 && c0 + j < N; ++j) o[j] = r[j];
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        } else {
+                            for (int j = 0; j < 16 && c0 + j < N; ++j) o[j] = r[j];
+                        }
                     }
                 }
             }
@@ -256,14 +271,35 @@ int dr_head_tc_prep(dr_model* m) {
     return DR_OK;
 }
 
-int dr_launch_heads_tc(dr_model* m, const float* S, int B, int T, float* out_local) {
+int dr_launch_heads_tc_dst(dr_model* m, const float* S, int B, int T, void* const* dst_ptrs, int n_dst, long long row0) {
     int N = m->M_loc * DR_Q;
     if (N == 0) return DR_OK;
+    if (n_dst < 1 || n_dst > 8) return dr_fail(m, DR_EINVAL, "peer-write head: 1..8 destinations");
+    HeadDst dst;
+    for (int w = 0; w < 8; ++w) dst.ptr[w] = (w < n_dst) ? reinterpret_cast<float*>(dst_ptrs[w]) : nullptr;
+    dst.world = n_dst; dst.ld = m->cfg.world * N; dst.col0 = m->cfg.rank * N; dst.row0 = row0;
     int n_chunks = (N + kNC - 1) / kNC;
     DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
     dim3 grid((B + 127) / 128, T);
     dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
-        S, m->d_himg, m->d_hb, m->d_p, out_local, B, T, dr_s_rows(B), N, n_chunks,
+        S, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B), N, n_chunks,
+        m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
+
+int dr_launch_heads_tc(dr_model* m, const float* S, int B, int T, float* out_local) {
+    int N = m->M_loc * DR_Q;
+    if (N == 0) return DR_OK;
+    HeadDst dst;
+    for (int w = 0; w < 8; ++w) dst.ptr[w] = nullptr;
+    dst.ptr[0] = out_local; dst.world = 1; dst.ld = N; dst.col0 = 0; dst.row0 = 0;
+    int n_chunks = (N + kNC - 1) / kNC;
+    DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
+    dim3 grid((B + 127) / 128, T);
+    dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
+        S, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B), N, n_chunks,
         m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;

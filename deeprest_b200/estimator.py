@@ -55,6 +55,8 @@ class QuantileRNN:
         self.quantiles, self.dropout_p = tuple(float(q) for q in quantiles), float(dropout)
         self.training = True                     # nn.Module default
         self._pg = process_group
+        self._engine, self._peer = engine, None
+        self.fused_gather = True                 # sharded runs: head kernel stores into every rank's forecast tensor
         if process_group is not None or (world or 1) > 1:
             import torch.distributed as dist
             rank = dist.get_rank(process_group) if rank is None else rank
@@ -187,9 +189,19 @@ class QuantileRNN:
             self._bind_stream()
             _lib.check(h, lib.dr_interleave_dev(h, gathered.data_ptr(), out.shape[0], T, out.data_ptr()))
 
+        def heads_p2p_fn(S, bn, ptrs, row0):
+            self._bind_stream()
+            _lib.check(h, lib.dr_forward_heads_p2p_dev(h, S.data_ptr(), bn, T, ptrs, self.world, row0))
+
+        peer = None
+        if self.input_size <= 64 and self._engine != "ffma" and self.fused_gather:
+            from .sharding import PeerBuffers
+            if self._peer is None:
+                self._peer = PeerBuffers(self._pg)
+            peer = self._peer
         return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
                                s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
-                               interleave_fn=interleave_fn, group=self._pg)
+                               interleave_fn=interleave_fn, group=self._pg, peer=peer, heads_p2p_fn=heads_p2p_fn)
 
     # ---- steps either side of the path ----------------------------------------
     def forward_series(self, series, window_size, stride=1):

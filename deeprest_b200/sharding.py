@@ -26,7 +26,36 @@ def _chunks(B, is_cuda):
     return [(b0, min(B, b0 + step)) for b0 in range(0, B, step)]
 
 
-def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interleave_fn, group=None):
+class PeerBuffers:
+    """Full forecast tensors [B,T,M,Q] in peer-mapped symmetric memory (torch.distributed._symmetric_memory):
+    every rank can store into every rank's buffer, which lets the head kernel write the stacked forecast tensor on all
+    GPUs directly over NVLink (dr_forward_heads_p2p_dev) instead of all-gather + interleave.  Two buffers per shape
+    alternate, so a result stays valid while the next forward runs."""
+
+    def __init__(self, group):
+        self.group, self.cache, self.failed = group, {}, None
+
+    def acquire(self, shape, device):
+        import ctypes as C
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        key = (tuple(shape), str(device))
+        ent = self.cache.get(key)
+        if ent is None:
+            bufs = []
+            for _ in range(2):
+                t = symm.empty(tuple(shape), dtype=torch.float32, device=device)
+                hdl = symm.rendezvous(t, self.group)
+                ptrs = (C.c_void_p * hdl.world_size)(*[int(p) for p in hdl.buffer_ptrs])
+                bufs.append((t, hdl, ptrs))
+            ent = self.cache[key] = {"bufs": bufs, "next": 0}
+        t, hdl, ptrs = ent["bufs"][ent["next"]]
+        ent["next"] ^= 1
+        return t, hdl, ptrs
+
+
+def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interleave_fn, group=None,
+                    peer=None, heads_p2p_fn=None):
     """x [B,T,F] (replicated on every rank) -> forecasts [B,T,world*m_local,q] on every rank.
 
     local_fn(x_c, S_c, out_local_c), heads_fn(S_c, out_local_c), interleave_fn(gathered_c, out_c) act on
@@ -35,7 +64,17 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
     import torch.distributed as dist
 
     B, T = int(x.shape[0]), int(x.shape[1])
-    out = torch.empty((B, T, world * m_local, q), device=x.device, dtype=torch.float32)
+    p2p = None
+    if peer is not None and heads_p2p_fn is not None and x.is_cuda and peer.failed is None:
+        try:
+            p2p = peer.acquire((B, T, world * m_local, q), x.device)
+        except Exception as exc:                     # no symmetric memory on this system: NCCL all-gather path
+            peer.failed = repr(exc)
+    if p2p is not None:
+        out, hdl, ptrs = p2p
+        hdl.barrier(channel=0)                       # every rank is done with the previous contents of this buffer
+    else:
+        out = torch.empty((B, T, world * m_local, q), device=x.device, dtype=torch.float32)
     chunks = _chunks(B, x.is_cuda)
     overlap = x.is_cuda and len(chunks) > 1
     if overlap:
@@ -48,11 +87,14 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
         bn = b1 - b0
         S = torch.empty((int(s_elems(bn)),), device=x.device, dtype=torch.float32)
         out_local = torch.empty((bn, T, m_local, q), device=x.device, dtype=torch.float32)
-        flat = torch.empty((world * bn, T, m_local, q), device=x.device, dtype=torch.float32)
+        flat = None if p2p is not None else torch.empty((world * bn, T, m_local, q), device=x.device, dtype=torch.float32)
 
         def pipeline():
             local_fn(x[b0:b1], S, out_local)                       # local bi-GRUs: partial S, own-expert head term
             dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)  # head i needs every other expert's output
+            if p2p is not None:                                    # heads + all-gather + interleave in ONE kernel:
+                heads_p2p_fn(S, bn, ptrs, b0)                      # stores go to every rank's out[b0:b1] over NVLink
+                return
             heads_fn(S, out_local)                                 # + (A_i/(M-1))·S + b_i
             dist.all_gather_into_tensor(flat, out_local, group=group)   # rank-major concatenation along dim 0
             interleave_fn(flat.view(world, bn, T, m_local, q), out[b0:b1])   # -> reference layout [B,T,M,Q]
@@ -63,10 +105,13 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
                 side.wait_event(start)
                 pipeline()
             for t in (S, out_local, flat, out, x):
-                t.record_stream(side)
+                if t is not None:
+                    t.record_stream(side)
         else:
             pipeline()
     if overlap:
         for side in sides:
             main.wait_stream(side)
+    if p2p is not None:
+        hdl.barrier(channel=1)                       # every rank's stores into this rank's buffer have landed
     return out

@@ -118,6 +118,13 @@ int  dr_forward_local_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T,
                           float* S_dev, float* out_local_dev);
 int  dr_forward_heads_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
                           float* out_local_dev);
+/*   3'+4' fused (tcgen05 engine): instead of steps 3-4, dr_forward_heads_p2p_dev writes this rank's forecasts straight
+ *      into EVERY rank's full tensor out[Bfull,T,M,Q] (reference layout): out_ptrs[w] is rank w's buffer, peer-mapped
+ *      into this process (CUDA IPC / torch symmetric memory); rows row0..row0+B-1.  The stores to peers travel over
+ *      NVLink from inside the head kernel — no all-gather, no interleave.  The caller barriers across ranks before
+ *      (buffers free) and after (writes landed). */
+int  dr_forward_heads_p2p_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
+                              void* const* out_ptrs, int32_t n_ptrs, int64_t row0);
 int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int32_t T,
                           float* out_dev);
 
