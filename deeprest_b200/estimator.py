@@ -56,7 +56,10 @@ class QuantileRNN:
         self.training = True                     # nn.Module default
         self._pg = process_group
         self._engine, self._peer = engine, None
-        self.fused_gather = True                 # sharded runs: head kernel stores into every rank's forecast tensor
+        # sharded runs: let the head kernel store into every rank's forecast tensor (peer memory) instead of NCCL
+        # all-gather + interleave.  Measured: +7 % at 2 GPUs, but at 8 GPUs its 64-byte peer stores reach only about a
+        # third of NCCL's all-gather bandwidth (49.0 vs 37.1 ms/step, profiles/r01_run_r / r01_run_l) -> default off there.
+        self.fused_gather = None                 # None = auto (world <= 2)
         if process_group is not None or (world or 1) > 1:
             import torch.distributed as dist
             rank = dist.get_rank(process_group) if rank is None else rank
@@ -194,7 +197,8 @@ class QuantileRNN:
             _lib.check(h, lib.dr_forward_heads_p2p_dev(h, S.data_ptr(), bn, T, ptrs, self.world, row0))
 
         peer = None
-        if self.input_size <= 64 and self._engine != "ffma" and self.fused_gather:
+        fused = (self.world <= 2) if self.fused_gather is None else bool(self.fused_gather)
+        if self.input_size <= 64 and self._engine != "ffma" and fused:
             from .sharding import PeerBuffers
             if self._peer is None:
                 self._peer = PeerBuffers(self._pg)
