@@ -7,7 +7,7 @@ Public surface:
   * ``synth``             counter-based synthetic trace/weight generator
 The CUDA library is loaded lazily on first use and there is no CPU fallback.
 """
-from . import layout, synth  # noqa: F401
+from . import featurize, layout, synth  # noqa: F401
 from .estimator import QuantileRNN, sliding_window  # noqa: F401
 
-__all__ = ["QuantileRNN", "sliding_window", "layout", "synth"]
+__all__ = ["QuantileRNN", "sliding_window", "layout", "synth", "featurize"]

@@ -139,5 +139,55 @@ def main():
     print("g8_window_norm:", win.shape, lo, hi)
 
 
+def synthetic_buckets(seed, n_buckets=6):
+    """Small random call trees over a social-network-like component set (own generator, counter based)."""
+    comps = ["nginx-thrift", "compose-post-service", "text-service", "user-mention-service", "media-mongodb", "post-storage"]
+    ops = ["Compose", "Upload", "Read", "Store", "Find"]
+    u = iter(synth.uniform(seed, 20000))
+
+    def tree(depth):
+        node = {"component": comps[int(next(u) * len(comps))], "operation": ops[int(next(u) * len(ops))], "children": []}
+        if depth < 3:
+            for _ in range(int(next(u) * 3)):
+                node["children"].append(tree(depth + 1))
+        return node
+
+    buckets = []
+    for _ in range(n_buckets):
+        traces = [tree(0) for _ in range(1 + int(next(u) * 6))]
+        metrics = [{"component": c, "resource": r, "value": float(next(u) * 100)} for c in comps[:3] for r in ("cpu", "memory")]
+        buckets.append({"traces": traces, "metrics": metrics})
+    return buckets
+
+
+def featurize_golden():
+    """G9 — the featurizer (featurize.py:11-101) run on synthetic buckets AND on the reference's own shipped sample."""
+    import json
+    import pickle
+    import featurize as ref_feat                       # the reference module (functions only; its script part is under __main__)
+    cases = {"synthetic": synthetic_buckets(123)}
+    with open("/root/reference/resource-estimation/raw_data.pkl", "rb") as f:
+        cases["shipped_sample"] = pickle.load(f)
+    out = {}
+    for name, raw in cases.items():
+        Mf = {}
+        for bucket in raw:
+            Mf = ref_feat.construct_feature_space(Mf, bucket["traces"])
+        traffic = np.asarray([ref_feat.extract_feature(Mf, bucket["traces"]) for bucket in raw])
+        inv = {}
+        for bucket in raw:
+            c = ref_feat.count_invocations(bucket["traces"])
+            for k, v in c.items():
+                inv.setdefault(k, [0] * len(raw))
+        for i, bucket in enumerate(raw):
+            for k, v in ref_feat.count_invocations(bucket["traces"]).items():
+                inv[k][i] = v
+        out[name] = {"raw": raw, "keys": list(Mf.keys()), "traffic": traffic.tolist(), "invocations": inv}
+    with open(os.path.join(OUT, "g9_featurize.json"), "w") as f:
+        json.dump(out, f)
+    print("g9_featurize:", {k: (len(v["keys"]), len(v["raw"])) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     main()
+    featurize_golden()
