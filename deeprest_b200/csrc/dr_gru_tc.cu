@@ -459,7 +459,9 @@ __global__ void dr_tc_pack_w_kernel(const float* __restrict__ blob, DrBlobOffset
         const float* w = ex + off.w_ih[d] + (size_t)(gate * DR_H + unit) * F;
         for (int j = 0; j < 8; ++j) {
             int k = chunk * 8 + j;
-            v[j] = (k < F) ? w[k] * mask[(size_t)e * F + k] : 0.0f;     // mask folded: W_ih' = W_ih diag(mask)
+            // mask folded: W_ih' = W_ih diag(mask).  The folded weights are O(1e-3): scaled by 2^5 (and x by 2^-5, exact)
+            // so that the fp16 lo parts of both operands stay clear of the subnormal range
+            v[j] = (k < F) ? w[k] * mask[(size_t)e * F + k] * 32.0f : 0.0f;
         }
     } else {                                // h-part rows: [r | z | gh_n] -> torch gate index (0, 1, 2)
         const float* w = ex + off.w_hh[d] + (size_t)(grp * DR_H + unit) * DR_H + (kk - 1) * 64;
@@ -494,7 +496,7 @@ __global__ void dr_tc_pack_x_kernel(const float* __restrict__ x, uint8_t* __rest
     float v[8];
     for (int j = 0; j < 8; ++j) {
         int f = chunk * 8 + j;
-        v[j] = (b < B && f < F) ? x[(size_t)b * xbs + (size_t)t * F + f] : 0.0f;
+        v[j] = (b < B && f < F) ? x[(size_t)b * xbs + (size_t)t * F + f] * 0.03125f : 0.0f;   // x * 2^-5, see dr_tc_pack_w_kernel
     }
     uint32_t hi[4], lo[4];
     for (int j = 0; j < 4; ++j) {

@@ -27,6 +27,9 @@ constexpr uint32_t kABlk = 128 * 128;               // A block: 128 rows x 64 K 
 constexpr uint32_t kAHalf = 4 * kABlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one K-half)
 constexpr uint32_t kBBlk = kNC * 128;               // B block: 96 rows x 64 K fp16
 constexpr uint32_t kBTile = 4 * kBBlk;              // hi kb0, hi kb1, lo kb0, lo kb1  (one chunk, one K-half)
+// The mean-term weights A/(M-1) are O(1e-4): their fp16 lo part would fall into the subnormals (13 good bits in all).
+// They are pre-scaled by 2^12 (exact) before the split and the accumulators are scaled back in the epilogue.
+constexpr float kWScale = 4096.0f, kWUnscale = 1.0f / 4096.0f;
 constexpr uint32_t kPSlab = 4 * 16 * 128 * 4;       // own-expert partials of 16 columns: [dir*2+half][16][128 rows] fp32 = 32 KB
 constexpr uint32_t kHOffA = 0, kHOffB = kAHalf, kHOffP = kHOffB + 2 * kBTile, kHOffBar = kHOffP + 2 * kPSlab;
 constexpr uint32_t kHSmem = kHOffBar + 128;
@@ -140,7 +143,7 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                         if (col < N) {
                             const int e = col / DR_Q;
                             const float own = (pv[0][j] + pv[1][j]) + (pv[2][j] + pv[3][j]);
-                            val = own + __uint_as_float(v[j]) + hb[col];
+                            val = own + __uint_as_float(v[j]) * kWUnscale + hb[col];
                             if (dn_scale) val = fmaxf(val, clamp_min) * dn_scale[e] + dn_offset[e];
                         }
                         r[j] = val;
@@ -243,7 +246,7 @@ __global__ void dr_head_tc_pack_kernel(const float* __restrict__ abar, int N, ui
         float v0 = 0.f, v1 = 0.f;
         if (col < N) {
             const float* a = abar + (size_t)col * DR_2H + kh * 128 + c8 * 8 + 2 * j;
-            v0 = a[0]; v1 = a[1];
+            v0 = a[0] * kWScale; v1 = a[1] * kWScale;
         }
         __half h0, l0, h1, l1;
         split_f16(v0, h0, l0); split_f16(v1, h1, l1);
