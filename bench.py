@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--windows", type=int, default=1024)
     ap.add_argument("--seq-len", type=int, default=288)
     ap.add_argument("--features", type=int, default=64)
+    ap.add_argument("--gather", default="auto", choices=["auto", "kernel", "copy", "nccl"],
+                    help="multi-GPU forecast gather: K2 peer stores / DMA-engine 2-D peer copies / NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the bounded CPU sample")
     return ap.parse_args()
@@ -252,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
     model = QuantileRNN(input_size=F, num_metrics=M, engine=args.engine, device=local_rank,
                         process_group=pg, rank=rank, world=world).eval()
     model.load_blob(blob)
+    model.gather_mode = args.gather
     x_dev = x_host.to(dev)
     log(f"model ready: M={M} (local {M_loc}) B={B} T={T} F={F}")
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "dr_forward_local_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "dr_forward_heads_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_forward_heads_p2p_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int64]),
+    "dr_scatter_forecasts_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int64]),
     "dr_interleave_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_quantile_loss": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_quantile_loss_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

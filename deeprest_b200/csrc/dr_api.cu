@@ -288,6 +288,24 @@ int dr_forward_heads_p2p_dev(dr_model* m, const float* S, int32_t B, int32_t T, 
     return rc;
 }
 
+int dr_scatter_forecasts_dev(dr_model* m, const float* out_local, int32_t B, int32_t T, void* const* out_ptrs,
+                             int32_t n_ptrs, int64_t row0) {
+    if (check_handle(m)) return DR_EINVAL;
+    if (!out_local || !out_ptrs || n_ptrs != m->cfg.world || B < 1 || T < 1)
+        return dr_fail(m, DR_EINVAL, "dr_scatter_forecasts_dev: one destination per rank");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    const size_t nloc = (size_t)m->M_loc * DR_Q, ntot = nloc * m->cfg.world;
+    const size_t rows = (size_t)B * T;
+    for (int w = 0; w < n_ptrs; ++w) {
+        // peers first, starting with the next rank, so that the 8 ranks do not all target the same peer at once
+        int dstw = (m->cfg.rank + 1 + w) % n_ptrs;
+        float* dst = reinterpret_cast<float*>(out_ptrs[dstw]) + ((size_t)row0 * T) * ntot + (size_t)m->cfg.rank * nloc;
+        DR_CUDA(m, cudaMemcpy2DAsync(dst, ntot * sizeof(float), out_local, nloc * sizeof(float), nloc * sizeof(float), rows,
+                                     cudaMemcpyDeviceToDevice, m->stream));
+    }
+    return DR_OK;
+}
+
 int dr_interleave_dev(dr_model* m, const float* gathered, int32_t B, int32_t T, float* out) {
     if (check_handle(m)) return DR_EINVAL;
     if (!gathered || !out || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "bad argument");

@@ -59,7 +59,9 @@ class QuantileRNN:
         # sharded runs: let the head kernel store into every rank's forecast tensor (peer memory) instead of NCCL
         # all-gather + interleave.  Measured: +7 % at 2 GPUs, but at 8 GPUs its 64-byte peer stores reach only about a
         # third of NCCL's all-gather bandwidth (49.0 vs 37.1 ms/step, profiles/r01_run_r / r01_run_l) -> default off there.
-        self.fused_gather = None                 # None = auto (world <= 2)
+        # "kernel": K2 stores to the peers; "copy": strided 2-D peer copies by the DMA engines after K2; "nccl": all_gather
+        # + interleave kernel; "auto": kernel for world <= 2, copy otherwise.
+        self.gather_mode = "auto"
         if process_group is not None or (world or 1) > 1:
             import torch.distributed as dist
             rank = dist.get_rank(process_group) if rank is None else rank
@@ -197,7 +199,6 @@ class QuantileRNN:
             _lib.check(h, lib.dr_forward_heads_p2p_dev(h, S.data_ptr(), bn, T, ptrs, self.world, row0))
 
         peer = None
-        fused = (self.world <= 2) if self.fused_gather is None else bool(self.fused_gather)
         if self.input_size <= 64 and self._engine != "ffma" and fused:
             from .sharding import PeerBuffers
             if self._peer is None:

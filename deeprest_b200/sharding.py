@@ -55,7 +55,7 @@ class PeerBuffers:
 
 
 def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interleave_fn, group=None,
-                    peer=None, heads_p2p_fn=None):
+                    peer=None, heads_p2p_fn=None, scatter_fn=None):
     """x [B,T,F] (replicated on every rank) -> forecasts [B,T,world*m_local,q] on every rank.
 
     local_fn(x_c, S_c, out_local_c), heads_fn(S_c, out_local_c), interleave_fn(gathered_c, out_c) act on
@@ -65,7 +65,7 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
 
     B, T = int(x.shape[0]), int(x.shape[1])
     p2p = None
-    if peer is not None and heads_p2p_fn is not None and x.is_cuda and peer.failed is None:
+    if peer is not None and (heads_p2p_fn is not None or scatter_fn is not None) and x.is_cuda and peer.failed is None:
         try:
             p2p = peer.acquire((B, T, world * m_local, q), x.device)
         except Exception as exc:                     # no symmetric memory on this system: NCCL all-gather path
@@ -92,10 +92,13 @@ def sharded_forward(x, *, world, m_local, q, s_elems, local_fn, heads_fn, interl
         def pipeline():
             local_fn(x[b0:b1], S, out_local)                       # local bi-GRUs: partial S, own-expert head term
             dist.all_reduce(S, op=dist.ReduceOp.SUM, group=group)  # head i needs every other expert's output
-            if p2p is not None:                                    # heads + all-gather + interleave in ONE kernel:
+            if p2p is not None and heads_p2p_fn is not None:       # heads + all-gather + interleave in ONE kernel:
                 heads_p2p_fn(S, bn, ptrs, b0)                      # stores go to every rank's out[b0:b1] over NVLink
                 return
             heads_fn(S, out_local)                                 # + (A_i/(M-1))·S + b_i
+            if p2p is not None:                                    # strided 2-D peer copies by the DMA engines place the
+                scatter_fn(out_local, bn, ptrs, b0)                # columns into every rank's out[b0:b1]: no SM time
+                return
             dist.all_gather_into_tensor(flat, out_local, group=group)   # rank-major concatenation along dim 0
             interleave_fn(flat.view(world, bn, T, m_local, q), out[b0:b1])   # -> reference layout [B,T,M,Q]
 

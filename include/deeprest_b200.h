@@ -125,6 +125,11 @@ int  dr_forward_heads_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
  *      (buffers free) and after (writes landed). */
 int  dr_forward_heads_p2p_dev(dr_model* m, const float* S_dev, int32_t B, int32_t T,
                               void* const* out_ptrs, int32_t n_ptrs, int64_t row0);
+/*   4'' copy-engine variant of step 4: after dr_forward_heads_dev, dr_scatter_forecasts_dev places this rank's
+ *      out_local [B,T,M_loc,Q] into columns [rank*M_loc, ...) of EVERY rank's full tensor (rows row0..) with strided
+ *      2-D peer copies — all-gather and interleave done by the DMA engines, no SM time. Same barrier rules as 3'+4'. */
+int  dr_scatter_forecasts_dev(dr_model* m, const float* out_local_dev, int32_t B, int32_t T,
+                              void* const* out_ptrs, int32_t n_ptrs, int64_t row0);
 int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int32_t T,
                           float* out_dev);
 

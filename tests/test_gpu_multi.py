@@ -32,13 +32,13 @@ def _worker(rank, world, port, path, engine, fused):
         x = torch.from_numpy(synth.windows(5, B, T, F, "diurnal")).cuda()
         model = QuantileRNN(F, M, engine=engine, device=rank, process_group=dist.group.WORLD).eval()
         model.load_blob(blob)
-        model.fused_gather = fused
+        model.gather_mode = fused
         out = model(x)
         out2 = model(x)                      # second call: exercises buffer reuse / barriers of the peer-write path
         torch.cuda.synchronize()
         assert torch.equal(out, out2) or float((out - out2).abs().max()) < 1e-6
         np.save(f"{path}.{rank}.npy", out.cpu().numpy())
-        used = bool(fused and model._peer is not None and model._peer.failed is None)
+        used = bool(fused != "nccl" and model._peer is not None and model._peer.failed is None)
         with open(f"{path}.{rank}.txt", "w") as f:
             f.write(f"{used} {None if model._peer is None else model._peer.failed}")
         model.close()
@@ -46,7 +46,7 @@ def _worker(rank, world, port, path, engine, fused):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("engine,fused", [("tcgen05", True), ("tcgen05", False), ("ffma", False)])
+@pytest.mark.parametrize("engine,fused", [("tcgen05", "kernel"), ("tcgen05", "copy"), ("tcgen05", "nccl"), ("ffma", "copy"), ("ffma", "nccl")])
 def test_two_gpu_sharded_forward_matches_single_gpu(tmp_path, engine, fused):
     import torch
     import torch.multiprocessing as mp
@@ -68,6 +68,6 @@ def test_two_gpu_sharded_forward_matches_single_gpu(tmp_path, engine, fused):
         assert out.shape == (B, T, M, 3)
         assert np.abs(out - ref1).max() < 2e-6, f"rank {r} vs single GPU: {np.abs(out - ref1).max()}"
         assert np.all(np.abs(out[:6] - ref) <= 1e-6 + 1e-4 * np.abs(ref))
-        if fused:       # the head kernel really stored into the peers' tensors (no silent NCCL fallback)
+        if fused != "nccl":       # the head kernel / the DMA engines really stored into the peers' tensors (no silent NCCL fallback)
             used, why = open(f"{path}.{r}.txt").read().split(" ", 1)
             assert used == "True", f"peer-write path not used: {why}"
