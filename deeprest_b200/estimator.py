@@ -198,8 +198,24 @@ class QuantileRNN:
             self._bind_stream()
             _lib.check(h, lib.dr_forward_heads_p2p_dev(h, S.data_ptr(), bn, T, ptrs, self.world, row0))
 
+        def scatter_fn(out_local, bn, ptrs, row0):
+            self._bind_stream()
+            _lib.check(h, lib.dr_scatter_forecasts_dev(h, out_local.data_ptr(), bn, T, ptrs, self.world, row0))
+
         peer = None
-        if self.input_size <= 64 and self._engine != "ffma" and fused:
+        mode = self.gather_mode
+        if mode == "auto":
+            mode = "kernel" if self.world <= 2 else "copy"
+        if mode == "kernel" and (self.input_size > 64 or self._engine == "ffma"):
+            mode = "copy"                    # peer stores from K2 need the tcgen05 head kernel
+        if mode == "copy":
+            from .sharding import PeerBuffers
+            if self._peer is None:
+                self._peer = PeerBuffers(self._pg)
+            return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
+                                   s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
+                                   interleave_fn=interleave_fn, group=self._pg, peer=self._peer, scatter_fn=scatter_fn)
+        if mode == "kernel":
             from .sharding import PeerBuffers
             if self._peer is None:
                 self._peer = PeerBuffers(self._pg)
