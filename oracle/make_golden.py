@@ -139,6 +139,38 @@ def main():
     print("g8_window_norm:", win.shape, lo, hi)
 
 
+def trained_golden():
+    """G10 — weights after actually TRAINING the reference for 60 Adam steps (estimate.py:65-74 loop, default
+    dropout) on a learnable synthetic task: the feature masks become peaky and the gates saturate the way a trained
+    DeepRest model's do.  The blob travels in the fixture (torch's RNG stream for dropout cannot be regenerated)."""
+    M, B, T, F = 2, 16, 60, 16
+    torch.manual_seed(1)
+    model = QuantileRNN(input_size=F, num_metrics=M)
+    x = synth.windows(31, B, T, F, "diurnal")
+    y = np.stack([np.clip(0.6 * x[:, :, 0] + 0.3 * x[:, :, 3], 0, 1), np.clip(x[:, :, 5] ** 2, 0, 1)], axis=-1).astype(np.float32)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    model.train()
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    for _ in range(60):
+        loss = model.quantile_loss(model(xt), yt)
+        opt.zero_grad(); loss.backward(); opt.step()
+    model.eval()
+    blob = layout.blob_from_state_dict(model.state_dict(), M, F)
+    xe = synth.windows(XSEED, 6, T, F, "diurnal")
+    with torch.no_grad():
+        out = model(torch.from_numpy(xe))
+        l = model.quantile_loss(out, torch.from_numpy(synth.labels(YSEED, 6, T, M))).item()
+    out64 = run_fp64(model, xe)
+    np.savez_compressed(os.path.join(OUT, "g10_trained.npz"), M=M, B=6, T=T, F=F, wsrc="torch", wscale=1.0, wseed=0,
+                        xseed=XSEED, yseed=YSEED, xkind="diurnal", out=out.numpy(), out64=out64, loss=np.float32(l),
+                        blob=blob, blob_sum=np.float64(blob.astype(np.float64).sum()),
+                        x_sum=np.float64(xe.astype(np.float64).sum()), torch_version=torch.__version__,
+                        train_loss=np.float32(loss.item()))
+    mk = torch.softmax(model.experts[0][1](torch.relu(model.experts[0][0](model.mask_init))), -1)
+    print(f"g10_trained: train loss {loss.item():.4f}, max mask {mk.max().item():.3f}, |out|max {out.abs().max().item():.3f}, "
+          f"fp32-fp64 {np.abs(out.numpy() - out64).max():.2e}")
+
+
 def synthetic_buckets(seed, n_buckets=6):
     """Small random call trees over a social-network-like component set (own generator, counter based)."""
     comps = ["nginx-thrift", "compose-post-service", "text-service", "user-mention-service", "media-mongodb", "post-storage"]
@@ -191,3 +223,4 @@ def featurize_golden():
 if __name__ == "__main__":
     main()
     featurize_golden()
+    trained_golden()
