@@ -346,6 +346,7 @@ def run_ours(args, rank, world, local_rank):
         "frac": achieved / peaks["tensor_tflops"], "traffic": traffic.get(model.last_engine),
         "peak_source": peaks["source"], "kernel_ms": gru_ms, "head_kernel_ms": head_ms,
         "kernel_share_of_step": gru_ms / ms_step if ms_step else None,
+        "launches_per_step": n_prof // max(args.steps, 1),
         "algorithmic_flops_per_launch": flops,
         "algorithmic_hbm_bytes_per_launch": algorithmic_hbm_bytes(M_loc, M, B, T, F),
         "hbm_gbs_if_ideal_bytes": algorithmic_hbm_bytes(M_loc, M, B, T, F) / (gru_ms * 1e-3) / 1e9 if gru_ms > 0 else None,
@@ -361,7 +362,8 @@ def run_ours(args, rank, world, local_rank):
                    "services": S, "experts": M, "windows": B, "seq_len": T, "features": F,
                    "parallelism": f"expert-shard x{world}" if world > 1 else "single GPU",
                    "batch_windows_per_sec": B / (ms_step * 1e-3), "engine": model.last_engine,
-                   "l2": "inputs+outputs (x 75 MB, S 302 MB, forecasts 453 MB) exceed the 126 MB L2; no flush needed"},
+                   "l2": (f"inputs+outputs per GPU (x {B * T * F * 4 / 1e6:.0f} MB, S {B * T * 256 * 4 / 1e6:.0f} MB, forecasts "
+                          f"{B * T * M * 3 * 4 / 1e6:.0f} MB) exceed the 126 MB L2; no flush between steps needed")},
         "clocks": clocks.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3},
