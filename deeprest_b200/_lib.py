@@ -57,6 +57,9 @@ SIGNATURES = {
     "dr_train_step": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_float, _FP]),
     "dr_train_step_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64,
                                     C.c_float, C.c_void_p, C.c_void_p]),
+    "dr_train_begin_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64,
+                                     C.c_float, C.c_void_p, C.c_void_p]),
+    "dr_train_advance": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "dr_get_grads": (C.c_int, [_H, _FP, C.c_size_t]),
     "dr_debug_read": (C.c_int, [_H, C.c_char_p, _FP, C.c_size_t]),
     "dr_tc_probe": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,

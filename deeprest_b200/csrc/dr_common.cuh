@@ -131,6 +131,9 @@ int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev
 // dr_train.cu
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);
+int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
+                        float lr, float* loss_dev, float* out_dev);
+int dr_train_advance_impl(dr_model* m, int* kind, void** ptr, long long* count, int* dtype);
 void dr_train_free(dr_model* m);
 // dr_head_tc.cu
 int dr_head_tc_prep(dr_model* m);

@@ -374,9 +374,20 @@ int gemm(dr_model* m, const Gemm& g, int batch) {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// The step is a resumable state machine: dr_train_advance runs kernels until the step is done or — on an
+// expert-sharded handle — a cross-rank sum is needed (S after the forward of a micro-batch, the loss scalar, the
+// head adjoint G-bar before the backward of a micro-batch).  The host performs that all-reduce on the returned
+// device buffer and calls advance again (torch.distributed in the Python host; NCCL in a C/Go host).  With
+// world == 1 no request is ever produced and dr_train_step simply drives the machine to completion.
+enum { TS_IDLE = 0, TS_MB_BEGIN, TS_AFTER_S, TS_AFTER_LOSS, TS_AFTER_G, TS_FINISH };
+
 struct dr_train_ws {
     float *xt, *gi, *rzn, *q, *hs, *dhout, *gh, *dhc, *S, *gbar, *dy, *P, *dmask;
     size_t cap_rows; int cap_B; int cap_T;
+    // state of the step in flight
+    int stage, pass, mb, n_mb, Bm, B, T;
+    const float *x, *y; const uint8_t* mask; uint64_t seed; float lr; float* loss_dev; float* out_dev;
 };
 
 static int ws_alloc(dr_model* m, float** p, size_t n) {
@@ -386,20 +397,18 @@ static int ws_alloc(dr_model* m, float** p, size_t n) {
     return DR_OK;
 }
 
-int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
-                       float lr, float* loss_dev, float* out_dev) {
-    const int F = m->cfg.F, Ml = m->M_loc, M = m->cfg.M, pe = m->off.per_expert;
-    const float p = m->cfg.dropout_p;
-    if (p >= 1.0f) return dr_fail(m, DR_EINVAL, "dropout_p must be < 1");
-    if (m->cfg.world != 1) return dr_fail(m, DR_EUNSUPPORTED, "dr_train_step: expert-sharded training is not built yet (world must be 1)");
-
+int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
+                        float lr, float* loss_dev, float* out_dev) {
+    const int F = m->cfg.F, Ml = m->M_loc, pe = m->off.per_expert;
+    if (m->cfg.dropout_p >= 1.0f) return dr_fail(m, DR_EINVAL, "dropout_p must be < 1");
     // micro-batch size from a memory budget (4.5 KB per expert-window-step-direction, see header)
     size_t per_window = (size_t)2 * Ml * T * (3 * DR_H * 2 + DR_H * 3) * sizeof(float);
     size_t budget = (size_t)24 << 30;
-    int Bm = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, budget / per_window));
+    int Bm = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, budget / std::max<size_t>(per_window, 1)));
     if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) Bm = std::min(B, v); }   // test hook
     dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
     if (!ws) { ws = new dr_train_ws(); memset(ws, 0, sizeof(*ws)); m->train_ws = ws; }
+    if (ws->stage != TS_IDLE) return dr_fail(m, DR_ESTATE, "a training step is already in flight on this handle");
     size_t rows = (size_t)T * Bm, E2 = (size_t)2 * Ml;
     if (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T) {
         int rc;
@@ -415,154 +424,219 @@ int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T
     }
     size_t nblob = (size_t)Ml * pe;
     if (!m->d_grad) {
-        DR_CUDA(m, cudaMalloc((void**)&m->d_grad, nblob * sizeof(float)));
-        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_m, nblob * sizeof(float)));
-        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_v, nblob * sizeof(float)));
+        DR_CUDA(m, cudaMalloc((void**)&m->d_grad, std::max<size_t>(nblob, 1) * sizeof(float)));
+        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_m, std::max<size_t>(nblob, 1) * sizeof(float)));
+        DR_CUDA(m, cudaMalloc((void**)&m->d_adam_v, std::max<size_t>(nblob, 1) * sizeof(float)));
         DR_CUDA(m, cudaMemsetAsync(m->d_adam_m, 0, nblob * sizeof(float), m->stream));
         DR_CUDA(m, cudaMemsetAsync(m->d_adam_v, 0, nblob * sizeof(float), m->stream));
         m->adam_step = 0;
     }
     DR_CUDA(m, cudaMemsetAsync(m->d_grad, 0, nblob * sizeof(float), m->stream));
     DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
-    double* acc = reinterpret_cast<double*>(m->d_loss);
-    DR_CUDA(m, cudaMemsetAsync(acc, 0, sizeof(double), m->stream));
-    cudaStream_t st = m->stream;
-    const float inv_n = 1.0f / ((float)M * (float)B * (float)T);
-    const size_t ed_stride = (size_t)Ml * rows;        // activations are [dir][e][(t,b)][...]
+    DR_CUDA(m, cudaMemsetAsync(m->d_loss, 0, sizeof(double), m->stream));
+    ws->stage = TS_MB_BEGIN; ws->pass = 0; ws->mb = 0; ws->Bm = Bm; ws->n_mb = (B + Bm - 1) / Bm; ws->B = B; ws->T = T;
+    ws->x = x; ws->y = y; ws->mask = mask; ws->seed = seed; ws->lr = lr; ws->loss_dev = loss_dev; ws->out_dev = out_dev;
+    return DR_OK;
+}
 
-    // ---------------- pass 1: forward over all micro-batches (out needs every window before the loss) ------------
-    // With more than one micro-batch the activations of earlier micro-batches are recomputed in pass 2.
-    const int n_mb = (B + Bm - 1) / Bm;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int mb = 0; mb < n_mb; ++mb) {
-            const int b0 = mb * Bm, bm = std::min(Bm, B - b0);
-            const size_t r = (size_t)T * bm;
-            const bool need_fwd = (pass == 0) || (n_mb > 1);
-            if (need_fwd) {
-                dr_time_major_kernel<<<nblk(r * F), 256, 0, st>>>(x, ws->xt, b0, bm, T, F);
-                for (int d = 0; d < 2; ++d) {
-                    float* gi = ws->gi + d * ed_stride * 3 * DR_H;
-                    float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
-                    float* q = ws->q + d * ed_stride * DR_H;
-                    float* hs = ws->hs + d * ed_stride * DR_H;
-                    // gi = (x*mask) W_ih^T + b_ih, all steps at once: the mask-folded rows live in d_wf? no — use W_ih and xm explicitly:
-                    // A(m=(t,b), k=f) = xt*mask is formed on the fly by scaling B instead: B(k=f, n=i) = W_ih[i][f]*mask[f] = d_wihm
-                    Gemm g{ws->xt, m->d_wihm + (size_t)d * Ml * 3 * DR_H * F, gi, (int)r, 3 * DR_H, F,
-                           F, 1, 1, F, 3 * DR_H, 1, 0, (long)3 * DR_H * F, (long)T * bm * 3 * DR_H, 0.0f};
-                    int rc = gemm(m, g, Ml);
-                    if (rc) return rc;
-                    size_t tot = (size_t)Ml * r * 3 * DR_H;
-                    dr_add_bias_kernel<<<nblk(tot), 256, 0, st>>>(gi, m->d_blob, m->off.b_ih[d], pe, r, tot);
-                    for (int s = 0; s < T; ++s) {
-                        const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
-                        const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
-                        if (s == 0) {
-                            DR_CUDA(m, cudaMemsetAsync(ws->gh, 0, (size_t)Ml * bm * 3 * DR_H * sizeof(float), st));
-                        } else {
-                            Gemm gh{hprev, m->d_blob + m->off.w_hh[d], ws->gh, bm, 3 * DR_H, DR_H,
-                                    DR_H, 1, 1, DR_H, 3 * DR_H, 1, (long)T * bm * DR_H, (long)pe, (long)bm * 3 * DR_H, 0.0f};
-                            rc = gemm(m, gh, Ml);
-                            if (rc) return rc;
-                        }
-                        size_t tg = (size_t)Ml * bm * DR_H;
-                        dr_gate_fwd_kernel<<<nblk(tg), 256, 0, st>>>(gi, ws->gh, hprev, m->d_blob, m->off.b_hh[d], pe,
-                                                                      rzn, q, hs, t, bm, T, tg);
-                    }
-                }
-                size_t ts = r * DR_2H;
-                dr_sum_experts_kernel<<<nblk(ts), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, mask, seed, p, ws->S, Ml, m->e_lo, B, b0, bm, T, ts);
-                if (pass == 0) {
-                    size_t tw = r * Ml * 32;
-                    dr_head_fwd_kernel<<<nblk(tw), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, mask, seed, p, m->d_ct, m->d_abar, m->d_hb,
-                                                                  out_dev, Ml, m->e_lo, B, b0, bm, T);
-                }
-                DR_CUDA(m, cudaGetLastError());
-                m->launches += 4 + 2 * (2 + 2 * T);
+// forward of micro-batch mb up to the local partial of S
+static int train_forward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
+    const int F = m->cfg.F, Ml = m->M_loc, pe = m->off.per_expert, T = ws->T, B = ws->B;
+    const float p = m->cfg.dropout_p;
+    cudaStream_t st = m->stream;
+    const size_t r = (size_t)T * bm;
+    const size_t ed_stride = (size_t)Ml * ws->cap_rows;
+    dr_time_major_kernel<<<nblk(r * F), 256, 0, st>>>(ws->x, ws->xt, b0, bm, T, F);
+    for (int d = 0; d < 2; ++d) {
+        float* gi = ws->gi + d * ed_stride * 3 * DR_H;
+        float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
+        float* q = ws->q + d * ed_stride * DR_H;
+        float* hs = ws->hs + d * ed_stride * DR_H;
+        // gi = x (W_ih diag(mask))^T + b_ih for all steps at once (the folded weights come from K0: d_wihm)
+        Gemm g{ws->xt, m->d_wihm + (size_t)d * Ml * 3 * DR_H * F, gi, (int)r, 3 * DR_H, F,
+               F, 1, 1, F, 3 * DR_H, 1, 0, (long)3 * DR_H * F, (long)T * bm * 3 * DR_H, 0.0f};
+        int rc = gemm(m, g, Ml);
+        if (rc) return rc;
+        size_t tot = (size_t)Ml * r * 3 * DR_H;
+        if (tot) dr_add_bias_kernel<<<nblk(tot), 256, 0, st>>>(gi, m->d_blob, m->off.b_ih[d], pe, r, tot);
+        for (int s = 0; s < T; ++s) {
+            const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
+            const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
+            if (s == 0) {
+                DR_CUDA(m, cudaMemsetAsync(ws->gh, 0, (size_t)Ml * bm * 3 * DR_H * sizeof(float), st));
+            } else {
+                Gemm gh{hprev, m->d_blob + m->off.w_hh[d], ws->gh, bm, 3 * DR_H, DR_H,
+                        DR_H, 1, 1, DR_H, 3 * DR_H, 1, (long)T * bm * DR_H, (long)pe, (long)bm * 3 * DR_H, 0.0f};
+                rc = gemm(m, gh, Ml);
+                if (rc) return rc;
             }
-            if (pass == 0) {
-                if (mb == n_mb - 1) {
-                    size_t n_rm = (size_t)B * T * M;
-                    unsigned blocks = std::min<unsigned>(nblk(n_rm), 148u * 8u);
-                    dr_loss_grad_kernel<<<blocks, 256, 0, st>>>(out_dev, y, ws->dy, n_rm, m->cfg.quantiles[0], m->cfg.quantiles[1],
-                                                                 m->cfg.quantiles[2], inv_n, acc);
-                    dr_finish_loss_kernel<<<1, 1, 0, st>>>(acc, (double)inv_n, loss_dev);
-                    DR_CUDA(m, cudaGetLastError());
-                    m->launches += 2;
-                }
-                continue;
-            }
-            // ---------------- pass 2: backward of this micro-batch ----------------
-            size_t ts = r * DR_2H;
-            dr_gbar_kernel<<<nblk(ts), 256, 0, st>>>(ws->dy, m->d_abar, ws->gbar, Ml, b0, bm, T, ts);
-            size_t td = (size_t)2 * Ml * r * DR_H;
-            // dhout is laid out [d][e][(t,b)][H] with the SAME (t,b) row stride as hs of this micro-batch
-            dr_dhout_kernel<<<nblk(td), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, mask, seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
-            {
-                int chunk = 2048;
-                dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
-                dr_head_grad_kernel<<<grid, DR_2H, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, ws->dy, mask, seed, p, m->d_grad, m->off.head_w,
-                                                             m->off.head_b, pe, 1.0f / (float)(M - 1), Ml, m->e_lo, B, b0, bm, T, chunk);
-            }
-            DR_CUDA(m, cudaGetLastError());
-            m->launches += 3;
-            for (int d = 0; d < 2; ++d) {
-                float* gi = ws->gi + d * ed_stride * 3 * DR_H;
-                float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
-                float* q = ws->q + d * ed_stride * DR_H;
-                float* hs = ws->hs + d * ed_stride * DR_H;
-                float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
-                DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
-                for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
-                    const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
-                    const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
-                    size_t tg = (size_t)Ml * bm * DR_H;
-                    dr_gate_bwd_kernel<<<nblk(tg), 256, 0, st>>>(rzn, gi, q, hprev, dho, ws->dhc, t, bm, T, tg);
-                    if (s > 0) {   // dh_{prev} = dh*z + dgh W_hh
-                        Gemm gd{rzn + (size_t)t * bm * 3 * DR_H, m->d_blob + m->off.w_hh[d], ws->dhc, bm, DR_H, 3 * DR_H,
-                                3 * DR_H, 1, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)pe, (long)bm * DR_H, 1.0f};
-                        int rc = gemm(m, gd, Ml);
-                        if (rc) return rc;
-                    }
-                }
-                // weight gradients over all (t,b) of the micro-batch
-                //  dW_hh += dgh^T h_prev : skip the step whose h_prev is the zero initial state
-                {
-                    const size_t skip = (size_t)bm;              // one time step of rows
-                    const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
-                    const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
-                    if (T > 1) {
-                        Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
-                                1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
-                        int rc = gemm(m, gw, Ml);
-                        if (rc) return rc;
-                    }
-                    Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
-                            (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
-                    int rc = gemm(m, gp, Ml);
-                    if (rc) return rc;
-                    dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
-                    int chunk = 1024;
-                    dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
-                    dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);
-                    dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(gi, m->d_grad, m->off.b_ih[d], pe, r, chunk);
-                    DR_CUDA(m, cudaGetLastError());
-                    m->launches += 3 + 2 * T;
-                }
-            }
+            size_t tg = (size_t)Ml * bm * DR_H;
+            if (tg) dr_gate_fwd_kernel<<<nblk(tg), 256, 0, st>>>(gi, ws->gh, hprev, m->d_blob, m->off.b_hh[d], pe, rzn, q, hs, t, bm, T, tg);
         }
     }
-    dr_mask_bwd_kernel<<<Ml, DR_H, F * sizeof(float), st>>>(m->d_blob, m->off, F, m->d_mask, ws->dmask, m->d_grad);
-    // ---------------- Adam ----------------
-    m->adam_step += 1;
-    const double b1 = 0.9, b2 = 0.999;
-    double bc1 = 1.0 - pow(b1, (double)m->adam_step), bc2 = 1.0 - pow(b2, (double)m->adam_step);
-    dr_adam_kernel<<<nblk(nblob), 256, 0, st>>>(m->d_blob, m->d_grad, m->d_adam_m, m->d_adam_v, nblob,
-                                                (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2, 1e-8f);
+    size_t ts = r * DR_2H;
+    dr_sum_experts_kernel<<<nblk(ts), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->mask, ws->seed, p, ws->S, Ml, m->e_lo, B, b0, bm, T, ts);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 2 + 2 * (2 + 2 * T);
+    return DR_OK;
+}
+
+// backward of micro-batch mb (G-bar already complete in ws->gbar)
+static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
+    const int F = m->cfg.F, Ml = m->M_loc, M = m->cfg.M, pe = m->off.per_expert, T = ws->T, B = ws->B;
+    const float p = m->cfg.dropout_p;
+    cudaStream_t st = m->stream;
+    const size_t r = (size_t)T * bm;
+    const size_t ed_stride = (size_t)Ml * ws->cap_rows;
+    size_t td = (size_t)2 * Ml * r * DR_H;
+    // dhout is laid out [d][e][(t,b)][H] with the (t,b) row stride of this micro-batch
+    if (td) dr_dhout_kernel<<<nblk(td), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, ws->mask, ws->seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
+    if (Ml) {
+        int chunk = 2048;
+        dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
+        dr_head_grad_kernel<<<grid, DR_2H, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, ws->dy, ws->mask, ws->seed, p, m->d_grad,
+                                                     m->off.head_w, m->off.head_b, pe, 1.0f / (float)(M - 1), Ml, m->e_lo, B, b0, bm, T, chunk);
+    }
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
-    int rc = dr_launch_prep(m);                 // the inference images follow the new weights
+    for (int d = 0; d < 2 && Ml; ++d) {
+        float* gi = ws->gi + d * ed_stride * 3 * DR_H;
+        float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
+        float* q = ws->q + d * ed_stride * DR_H;
+        float* hs = ws->hs + d * ed_stride * DR_H;
+        float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
+        DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
+        for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
+            const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
+            const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
+            size_t tg = (size_t)Ml * bm * DR_H;
+            dr_gate_bwd_kernel<<<nblk(tg), 256, 0, st>>>(rzn, gi, q, hprev, dho, ws->dhc, t, bm, T, tg);
+            if (s > 0) {   // dh_{prev} = dh*z + dgh W_hh
+                Gemm gd{rzn + (size_t)t * bm * 3 * DR_H, m->d_blob + m->off.w_hh[d], ws->dhc, bm, DR_H, 3 * DR_H,
+                        3 * DR_H, 1, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)pe, (long)bm * DR_H, 1.0f};
+                int rc = gemm(m, gd, Ml);
+                if (rc) return rc;
+            }
+        }
+        // weight gradients over all (t,b) of the micro-batch; dW_hh skips the step whose h_prev is the zero initial state
+        const size_t skip = (size_t)bm;
+        const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
+        const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
+        if (T > 1) {
+            Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
+                    1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
+            int rc = gemm(m, gw, Ml);
+            if (rc) return rc;
+        }
+        Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
+                (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
+        int rc = gemm(m, gp, Ml);
+        if (rc) return rc;
+        dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
+        int chunk = 1024;
+        dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
+        dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);
+        dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(gi, m->d_grad, m->off.b_ih[d], pe, r, chunk);
+        DR_CUDA(m, cudaGetLastError());
+        m->launches += 3 + 2 * T;
+    }
+    return DR_OK;
+}
+
+// kind: 0 = step finished, 1 = all-reduce(sum) `count` elements at `ptr` (dtype 0 = fp32, 1 = fp64) across the ranks, then call again
+int dr_train_advance_impl(dr_model* m, int* kind, void** ptr, long long* count, int* dtype) {
+    dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
+    if (!ws || ws->stage == TS_IDLE) return dr_fail(m, DR_ESTATE, "dr_train_advance without dr_train_begin");
+    const int Ml = m->M_loc, M = m->cfg.M, T = ws->T, B = ws->B, F = m->cfg.F, pe = m->off.per_expert;
+    const float p = m->cfg.dropout_p;
+    const bool sharded = m->cfg.world > 1;
+    cudaStream_t st = m->stream;
+    const float inv_n = 1.0f / ((float)M * (float)B * (float)T);
+    double* acc = reinterpret_cast<double*>(m->d_loss);
+    *kind = 0; *ptr = nullptr; *count = 0; *dtype = 0;
+    for (;;) {
+        const int b0 = ws->mb * ws->Bm, bm = std::min(ws->Bm, B - b0);
+        const size_t r = (size_t)T * bm;
+        const size_t ed_stride = (size_t)Ml * ws->cap_rows;
+        switch (ws->stage) {
+        case TS_MB_BEGIN: {
+            // pass 0 runs every forward (the loss needs all windows); pass 1 recomputes a micro-batch's activations
+            // only when there is more than one micro-batch (otherwise they are still in the workspace)
+            const bool need_fwd = (ws->pass == 0) || (ws->n_mb > 1);
+            ws->stage = TS_AFTER_S;
+            if (need_fwd) {
+                int rc = train_forward_mb(m, ws, b0, bm);
+                if (rc) { ws->stage = TS_IDLE; return rc; }
+                if (sharded) { *kind = 1; *ptr = ws->S; *count = (long long)(r * DR_2H); *dtype = 0; return DR_OK; }
+            }
+            break;
+        }
+        case TS_AFTER_S: {
+            if (ws->pass == 0) {
+                size_t tw = r * Ml * 32;
+                if (tw) dr_head_fwd_kernel<<<nblk(tw), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->S, ws->mask, ws->seed, p, m->d_ct,
+                                                                      m->d_abar, m->d_hb, ws->out_dev, Ml, m->e_lo, B, b0, bm, T);
+                m->launches += 1;
+                if (ws->mb + 1 < ws->n_mb) { ws->mb += 1; ws->stage = TS_MB_BEGIN; break; }
+                size_t n_rm = (size_t)B * T * Ml;              // local metrics; the mean runs over the GLOBAL M*B*T (inv_n)
+                unsigned blocks = std::max(1u, std::min<unsigned>(nblk(n_rm), 148u * 8u));
+                dr_loss_grad_kernel<<<blocks, 256, 0, st>>>(ws->out_dev, ws->y, ws->dy, n_rm, m->cfg.quantiles[0], m->cfg.quantiles[1],
+                                                             m->cfg.quantiles[2], inv_n, acc);
+                DR_CUDA(m, cudaGetLastError());
+                m->launches += 1;
+                ws->stage = TS_AFTER_LOSS;
+                if (sharded) { *kind = 1; *ptr = acc; *count = 1; *dtype = 1; return DR_OK; }
+            } else {
+                size_t ts = r * DR_2H;
+                dr_gbar_kernel<<<nblk(ts), 256, 0, st>>>(ws->dy, m->d_abar, ws->gbar, Ml, b0, bm, T, ts);
+                DR_CUDA(m, cudaGetLastError());
+                m->launches += 1;
+                ws->stage = TS_AFTER_G;
+                if (sharded) { *kind = 1; *ptr = ws->gbar; *count = (long long)ts; *dtype = 0; return DR_OK; }
+            }
+            break;
+        }
+        case TS_AFTER_LOSS:
+            dr_finish_loss_kernel<<<1, 1, 0, st>>>(acc, (double)inv_n, ws->loss_dev);
+            m->launches += 1;
+            ws->pass = 1; ws->mb = 0; ws->stage = TS_MB_BEGIN;
+            break;
+        case TS_AFTER_G: {
+            int rc = train_backward_mb(m, ws, b0, bm);
+            if (rc) { ws->stage = TS_IDLE; return rc; }
+            if (ws->mb + 1 < ws->n_mb) { ws->mb += 1; ws->stage = TS_MB_BEGIN; } else ws->stage = TS_FINISH;
+            break;
+        }
+        case TS_FINISH: {
+            size_t nblob = (size_t)Ml * pe;
+            if (Ml) dr_mask_bwd_kernel<<<Ml, DR_H, F * sizeof(float), st>>>(m->d_blob, m->off, F, m->d_mask, ws->dmask, m->d_grad);
+            m->adam_step += 1;                      // torch.optim.Adam defaults (estimate.py:61)
+            const double b1 = 0.9, b2 = 0.999;
+            double bc1 = 1.0 - pow(b1, (double)m->adam_step), bc2 = 1.0 - pow(b2, (double)m->adam_step);
+            if (nblob) dr_adam_kernel<<<nblk(nblob), 256, 0, st>>>(m->d_blob, m->d_grad, m->d_adam_m, m->d_adam_v, nblob,
+                                                                   (float)(ws->lr / bc1), (float)(1.0 / sqrt(bc2)), (float)b1, (float)b2, 1e-8f);
+            DR_CUDA(m, cudaGetLastError());
+            m->launches += 2;
+            ws->stage = TS_IDLE;
+            int rc = dr_launch_prep(m);             // the inference images follow the new weights
+            if (rc) return rc;
+            return dr_tc_prep_weights(m);
+        }
+        default:
+            ws->stage = TS_IDLE;
+            return dr_fail(m, DR_ESTATE, "corrupt training state");
+        }
+    }
+}
+
+int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
+                       float lr, float* loss_dev, float* out_dev) {
+    if (m->cfg.world != 1)
+        return dr_fail(m, DR_ESTATE, "dr_train_step needs world == 1; sharded handles drive dr_train_begin_dev / dr_train_advance");
+    int rc = dr_train_begin_impl(m, x, y, B, T, mask, seed, lr, loss_dev, out_dev);
     if (rc) return rc;
-    return dr_tc_prep_weights(m);
+    int kind; void* ptr; long long count; int dtype;
+    return dr_train_advance_impl(m, &kind, &ptr, &count, &dtype);
 }
 
 extern "C" {
@@ -600,6 +674,24 @@ int dr_train_step(dr_model* m, const float* x, const float* y, int32_t B, int32_
     DR_CUDA(m, cudaMemcpyAsync(loss_out, m->d_loss + 4, sizeof(float), cudaMemcpyDeviceToHost, m->stream));
     DR_CUDA(m, cudaStreamSynchronize(m->stream));
     return DR_OK;
+}
+
+int dr_train_begin_dev(dr_model* m, const float* x_dev, const float* y_dev, int32_t B, int32_t T,
+                       const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev, float* out_dev) {
+    if (!m) return DR_EINVAL;
+    if (!x_dev || !y_dev || !loss_dev || !out_dev || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "dr_train_begin_dev: bad argument");
+    if (!m->loaded) return dr_fail(m, DR_ESTATE, "train step before dr_load_weights");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    return dr_train_begin_impl(m, x_dev, y_dev, B, T, dropout_mask_dev, seed, lr, loss_dev, out_dev);
+}
+
+int dr_train_advance(dr_model* m, int32_t* kind, void** ptr, int64_t* count, int32_t* dtype) {
+    if (!m || !kind || !ptr || !count || !dtype) return DR_EINVAL;
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    int k = 0, dt = 0; void* p = nullptr; long long c = 0;
+    int rc = dr_train_advance_impl(m, &k, &p, &c, &dt);
+    *kind = k; *ptr = p; *count = c; *dtype = dt;
+    return rc;
 }
 
 int dr_get_grads(dr_model* m, float* host_blob, size_t n) {

@@ -278,6 +278,41 @@ class QuantileRNN:
                                                     C.c_uint64(int(seed)), C.c_float(lr), C.byref(loss)))
         return float(loss.value)
 
+    def train_step_sharded(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0):
+        """Expert-sharded training step (world > 1).  ``inputs`` [B,T,F] and ``labels`` [B,T,M] are the full tensors
+        (replicated); each rank trains its own experts.  The library's step is a state machine that asks for three kinds
+        of cross-rank sums (S, the loss scalar, the head adjoint); they run here through torch.distributed on the device
+        buffers.  Returns the (global) loss."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device)
+        x = torch.as_tensor(inputs, dtype=torch.float32).to(dev).contiguous()
+        lo, hi = self.rank * self.m_local, (self.rank + 1) * self.m_local
+        y = torch.as_tensor(labels, dtype=torch.float32)[:, :, lo:hi].to(dev).contiguous()
+        B, T, _ = x.shape
+        mask = None
+        if dropout_mask is not None:
+            mask = torch.as_tensor(np.ascontiguousarray(dropout_mask, np.uint8)).to(dev)
+        loss = torch.zeros((), device=dev, dtype=torch.float32)
+        out = torch.empty((B, T, self.m_local, layout.Q), device=dev, dtype=torch.float32)
+        self._bind_stream()
+        _lib.check(self._h, self._lib.dr_train_begin_dev(self._h, x.data_ptr(), y.data_ptr(), B, T,
+                                                         mask.data_ptr() if mask is not None else None,
+                                                         C.c_uint64(int(seed)), C.c_float(lr), loss.data_ptr(), out.data_ptr()))
+        kind, ptr, count, dtype = C.c_int32(), C.c_void_p(), C.c_int64(), C.c_int32()
+
+        class _Buf:                                   # a device buffer owned by the library, seen through the CUDA array interface
+            def __init__(self, p, n, f64):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if f64 else "<f4", "data": (p, False), "version": 2}
+
+        while True:
+            _lib.check(self._h, self._lib.dr_train_advance(self._h, C.byref(kind), C.byref(ptr), C.byref(count), C.byref(dtype)))
+            if kind.value == 0:
+                break
+            t = torch.as_tensor(_Buf(ptr.value, count.value, dtype.value == 1), device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._pg)
+        return float(loss.item())
+
     def grads(self):
         """Gradients of the last ``train_step`` as a blob in ``state_dict`` order."""
         out = np.zeros(layout.blob_size(self.num_metrics, self.input_size), np.float32)

@@ -153,6 +153,15 @@ int  dr_train_step_dev(dr_model* m, const float* x_dev, const float* y_dev, int3
                        const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev,
                        float* out_dev /* [B,T,M,Q] train-mode forecasts */);
 int  dr_get_grads     (dr_model* m, float* host_blob, size_t n_floats);
+/* Expert-sharded training (world > 1): the step is a resumable state machine.  dr_train_begin_dev takes the replicated
+ * x [B,T,F], this rank's label columns y [B,T,M_loc], the GLOBAL replayed mask (or NULL + seed) and out_dev
+ * [B,T,M_loc,Q]; dr_train_advance runs kernels until *kind == 0 (step done: local gradients applied by Adam) or
+ * *kind == 1: all-reduce(sum) `*count` elements at device pointer `*ptr` (*dtype 0 = fp32, 1 = fp64) across the
+ * ranks on the handle's stream, then call dr_train_advance again.  Requests: S after each micro-batch forward, the loss
+ * scalar, the head adjoint before each micro-batch backward.  No gradient all-reduce exists: weights are expert-local. */
+int  dr_train_begin_dev(dr_model* m, const float* x_dev, const float* y_local_dev, int32_t B, int32_t T,
+                        const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev, float* out_local_dev);
+int  dr_train_advance  (dr_model* m, int32_t* kind, void** ptr, int64_t* count, int32_t* dtype);
 
 /* ---- test/diagnostic access to prepared tensors (not on the hot path) ----
  * what: "mask" [M_loc,F] (qrnn.py:34), "S" (dr_s_elems floats, layout above) of the last
