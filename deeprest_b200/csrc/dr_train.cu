@@ -16,7 +16,8 @@
 
 namespace {
 
-constexpr int GT = 64, GK = 16, GLD = GT + 4;
+constexpr int GTM = 128, GTN = 64, GK = 16;          // CTA tile 128 x 64, K-chunk 16, 256 threads x (8 x 4) outputs
+constexpr int GLDA = GTM + 4, GLDB = GTN + 4;
 
 // C[z](m,n) = beta*C[z](m,n) + sum_k A[z](m,k) * B[z](k,n), arbitrary element strides
 struct Gemm {
@@ -27,41 +28,75 @@ struct Gemm {
     float beta;
 };
 
+// Register-tiled fp32 GEMM with a register-prefetched, double-buffered shared-memory pipeline.  Loads walk whichever of
+// (m|n) and k is the unit-stride dimension of each operand, so all five uses (input projection, per-step recurrent
+// products, dgh·W_hh, and the two weight-gradient reductions over (t,b)) stay coalesced without a transpose pass.
 __global__ void __launch_bounds__(256) dr_bgemm_kernel(Gemm g) {
-    __shared__ __align__(16) float As[GK][GLD];
-    __shared__ __align__(16) float Bs[GK][GLD];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    __shared__ __align__(16) float As[2][GK][GLDA];
+    __shared__ __align__(16) float Bs[2][GK][GLDB];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;        // ty: 8 rows each, tx: 4 cols each
+    const int m0 = blockIdx.y * GTM, n0 = blockIdx.x * GTN;
     const float* A = g.A + (size_t)blockIdx.z * g.bsA;
     const float* B = g.B + (size_t)blockIdx.z * g.bsB;
     float* C = g.C + (size_t)blockIdx.z * g.bsC;
     const bool a_m_fast = g.sam <= g.sak, b_n_fast = g.sbn <= g.sbk;
-    float acc[4][4] = {};
-    for (int k0 = 0; k0 < g.K; k0 += GK) {
+    float acc[8][4] = {};
+    float ra[8], rb[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                                  // A tile: 128 x 16 = 2048 elements, 8 per thread
+            int idx = tid + i * 256;
+            int m = a_m_fast ? idx % GTM : idx / GK, k = a_m_fast ? idx / GTM : idx % GK;
+            ra[i] = (m0 + m < g.M && k0 + k < g.K) ? A[(long)(m0 + m) * g.sam + (long)(k0 + k) * g.sak] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                                  // B tile: 16 x 64 = 1024 elements, 4 per thread
+            int idx = tid + i * 256;
+            int n = b_n_fast ? idx % GTN : idx / GK, k = b_n_fast ? idx / GTN : idx % GK;
+            rb[i] = (n0 + n < g.N && k0 + k < g.K) ? B[(long)(k0 + k) * g.sbk + (long)(n0 + n) * g.sbn] : 0.0f;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int idx = tid + i * 256;
+            int m = a_m_fast ? idx % GTM : idx / GK, k = a_m_fast ? idx / GTM : idx % GK;
+            As[buf][k][m] = ra[i];
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             int idx = tid + i * 256;
-            int m = a_m_fast ? idx % GT : idx / GK, k = a_m_fast ? idx / GT : idx % GK;
-            As[k][m] = (m0 + m < g.M && k0 + k < g.K) ? A[(long)(m0 + m) * g.sam + (long)(k0 + k) * g.sak] : 0.0f;
-            int n = b_n_fast ? idx % GT : idx / GK, kb = b_n_fast ? idx / GT : idx % GK;
-            Bs[kb][n] = (n0 + n < g.N && k0 + kb < g.K) ? B[(long)(k0 + kb) * g.sbk + (long)(n0 + n) * g.sbn] : 0.0f;
+            int n = b_n_fast ? idx % GTN : idx / GK, k = b_n_fast ? idx / GTN : idx % GK;
+            Bs[buf][k][n] = rb[i];
         }
-        __syncthreads();
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < g.K; k0 += GK) {
+        const bool more = k0 + GK < g.K;
+        if (more) fetch(k0 + GK);                                      // global loads in flight during the FFMAs
 #pragma unroll
         for (int kk = 0; kk < GK; ++kk) {
-            float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+            float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+            float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
-        __syncthreads();
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        int m = m0 + ty * 8 + i;
         if (m >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -364,7 +399,7 @@ inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t)
 
 int gemm(dr_model* m, const Gemm& g, int batch) {
     if (g.M <= 0 || g.N <= 0 || batch <= 0) return DR_OK;
-    dim3 grid((g.N + GT - 1) / GT, (g.M + GT - 1) / GT, batch);
+    dim3 grid((g.N + GTN - 1) / GTN, (g.M + GTM - 1) / GTM, batch);
     dr_bgemm_kernel<<<grid, 256, 0, m->stream>>>(g);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;

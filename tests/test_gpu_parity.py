@@ -212,3 +212,13 @@ def test_fused_clamp_and_denormalisation():
         + np.array([b for _, b in scales], np.float32)[None, None, :, None]
     assert np.abs(fused - ref).max() <= 1e-5 * np.abs(ref).max()
     assert np.abs(again - plain).max() < 1e-6
+
+
+@pytest.mark.parametrize("engine,M,B,T,F", [("tcgen05", 3, 700, 3, 20), ("ffma", 2, 600, 2, 100), ("tcgen05", 2, 1100, 2, 8)])
+def test_chunked_host_entry_point_matches_oracle(engine, M, B, T, F):
+    """dr_forward splits B >= 512 into 2-4 chunks on two compute streams + a copy stream; ragged last chunk."""
+    blob = synth.weights(77, M, F, 1.5)
+    x = synth.windows(12, B, T, F, "diurnal")
+    ref = oracle.forward(blob, x, M, F)
+    out = run(M, F, blob, x, engine)
+    assert_parity(out, ref, what=f"chunked host path {engine} B={B}")
