@@ -1,8 +1,8 @@
 // K1 (tensor-core engine) — fused bidirectional-GRU recurrence on tcgen05 / TMEM.
 //
 // Same contract as the FFMA engine (dr_gru_ffma.cu): for every local expert and both directions,
-// run the GRU over T steps (qrnn.py:33-42), add h_t into the cross-expert sum S and the
-// own-expert head term into out_local (qrnn.py:46-54 folded).
+// run the GRU over T steps (qrnn.py:33-42), add h_t into the cross-expert sum S and store the
+// own-expert head term into the partials workspace P for K2 (qrnn.py:46-54 folded).
 //
 // fp32 parity on 16-bit tensor cores: every operand is split v = hi + lo (two fp16, ~22 mantissa
 // bits) and each product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation in TMEM
@@ -19,8 +19,10 @@
 //   TMEM / CTA (512 col): 2 gate buffers x 128 fp32 columns [gi_n | r | z | gh_n] x 32 hidden units,
 //                         2 h-operand buffers x 128 columns (fp16 hi | lo, two per column): the
 //                         recurrent A operand never touches shared memory (tcgen05.st -> MMA.TS).
-//   warps               : 0-7 gate epilogue (TMEM lane quarter = w%4, hidden half = w/4),
-//                         8 MMA issuer (leader CTA), 9 bulk-copy producer.
+//   warps               : 0-7 gate epilogue (TMEM lane quarter = w%4, hidden half = w/4), 8 MMA issuer (leader CTA),
+//                         9 bulk-copy producer, 10-11 register donors (setmaxnreg: 216 regs for the epilogue warpgroups).
+//   work order          : tile-major (all expert-directions of a 256-window tile before the next), so the slice of S the
+//                         running clusters reduce into stays L2-resident.
 // Per step and hidden-quarter q:  x-part  D[:,0:96]   = x_t  * [W_in|W_ir|W_iz]_q^T   (A from smem)
 //                                 h-part  D[:,32:128] += h    * [W_hr|W_hz|W_hn]_q^T   (A from TMEM)
 // so r and z accumulate both parts while gi_n / gh_n stay separate (n = tanh(gi_n + r*gh_n)).
@@ -35,10 +37,10 @@ constexpr int kThreads = 384;          // 3 warpgroups: 2 x epilogue (warps 0-7)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kEpiWarps = 8;
 constexpr int kMmaWarp = 8, kLoadWarp = 9;
-constexpr uint32_t kBlk = 48 * 128;                 // one B block: 48 rows x 64 K (bf16) = 6 KB
+constexpr uint32_t kBlk = 48 * 128;                 // one B block: 48 rows x 64 K (fp16) = 6 KB
 constexpr uint32_t kQuarterBytes = 6 * kBlk;        // Wx_hi, Wx_lo, Wh_hi[2], Wh_lo[2]
 constexpr uint32_t kWBytes = 4 * kQuarterBytes;     // 147456 per CTA
-constexpr uint32_t kXTile = 128 * 128;              // one x part: 128 rows x 64 features (bf16) = 16 KB
+constexpr uint32_t kXTile = 128 * 128;              // one x part: 128 rows x 64 features (fp16) = 16 KB
 constexpr uint32_t kXStage = 2 * kXTile;            // hi + lo
 // TMEM columns
 constexpr uint32_t kG0 = 0, kHA = 256, kHB = 384;
@@ -482,7 +484,7 @@ __global__ void dr_tc_pack_w_kernel(const float* __restrict__ blob, DrBlobOffset
     *reinterpret_cast<uint4*>(base + lo_blk * kBlk + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// x [B,T,F] fp32 -> xtc [T][ntiles][2][hi|lo][128 rows x 64 K] swizzled bf16 images; zero padded
+// x [B,T,F] fp32 -> xtc [T][ntiles][2][hi|lo][128 rows x 64 K] swizzled fp16 images (scaled by 2^-5); zero padded
 __global__ void dr_tc_pack_x_kernel(const float* __restrict__ x, uint8_t* __restrict__ xtc,
                                     int B, int T, int F, int ntiles, long long xbs /* floats between window starts */) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

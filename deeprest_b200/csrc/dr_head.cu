@@ -1,6 +1,7 @@
 // K2 — cross-expert-mean head term, output layout, and the pinball loss.
 //
-//  dr_head_kernel      out_local[r, i*Q+q] += (A_i/(M-1))[q,:] · S[r,:] + b_i[q]     (qrnn.py:46-54, folded)
+//  dr_head_kernel      out_local[r, i*Q+q] += (A_i/(M-1))[q,:] · S[r,:] + b_i[q]     (qrnn.py:46-54, folded; FFMA engine —
+//                      the tcgen05 engine's K2 is dr_head_tc.cu)
 //  dr_interleave_kernel gathered[world][R][M_loc*Q] -> out[R][M*Q]                   (qrnn.py:55 layout)
 //  dr_loss_*           pinball loss                                                  (qrnn.py:58-67)
 #include "dr_common.cuh"
@@ -14,8 +15,7 @@ constexpr int TM = 64, TN = 64, TK = 32, LD = 68;
 __global__ void __launch_bounds__(256)
 dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, const float* __restrict__ hb,
                float* __restrict__ out, int B, int T, int BpS, int N,
-               const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min,
-               const float* __restrict__ P /* nullable: own-expert partials [T][BpS/128][ceil(N/16)][4][16][128] (tcgen05 engine) */) {
+               const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
     __shared__ __align__(16) float As[TK][LD];
     __shared__ __align__(16) float Bs[TK][LD];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -60,17 +60,7 @@ dr_head_kernel(const float* __restrict__ S, const float* __restrict__ abar, cons
         for (int j = 0; j < 4; ++j) {
             int col = c0 + tx * 4 + j;
             if (col < N) {
-                float own;
-                if (P) {              // sum the 2 directions x 2 hidden halves the recurrence kernel stored
-                    const int e = col / DR_Q, q = col % DR_Q;
-                    const int ngrp = (N + 15) >> 4;
-                    const float* pp = P + (((((size_t)t * (BpS >> 7) + (b >> 7)) * ngrp + (col >> 4)) * 4) * 16 + (col & 15)) * 128 + (b & 127);
-                    const size_t dh = (size_t)16 * 128;
-                    own = (pp[0] + pp[dh]) + (pp[2 * dh] + pp[3 * dh]);
-                    (void)e; (void)q;
-                } else {
-                    own = orow[col];  // FFMA engine: REDs already accumulated it in place
-                }
+                const float own = orow[col];          // the FFMA recurrence kernel REDs its own-expert term in place
                 float v = own + acc[i][j] + hb[col];
                 if (dn_scale) {       // estimate.py:96,102 — clamp the normalised forecast, then undo the min-max scaling
                     int e = col / DR_Q;
@@ -123,8 +113,7 @@ int dr_launch_heads(dr_model* m, const float* S, int B, int T, float* out_local)
     if (N == 0) return DR_OK;
     dim3 grid((B + TM - 1) / TM, T, (N + TN - 1) / TN);
     dr_head_kernel<<<grid, 256, 0, m->stream>>>(S, m->d_abar, m->d_hb, out_local, B, T, dr_s_rows(B), N,
-                                                m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp,
-                                                m->p_live ? m->d_p : nullptr);
+                                                m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;
