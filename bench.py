@@ -358,7 +358,9 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1] per GPU: {S} services x {B} windows x seq_len {T}, F={F}, fp32 inference",
+        "config": {"workload": (f"BASELINE configs[{1 if (world == 1 and S == 64) else 3 if (world == 8 and S == 1024) else 1}]"
+                                + ("" if (world == 1 and S == 64) or (world == 8 and S == 1024) else "-shaped, weak-scaled")
+                                + f": {S} services x {B} windows x seq_len {T}, F={F}, fp32 inference, {S // world} services per GPU"),
                    "services": S, "experts": M, "windows": B, "seq_len": T, "features": F,
                    "parallelism": f"expert-shard x{world}" if world > 1 else "single GPU",
                    "batch_windows_per_sec": B / (ms_step * 1e-3), "engine": model.last_engine,
