@@ -1,8 +1,9 @@
 """Expert-sharded forward orchestration, backend agnostic.
 
 The exchange steps of the path — one ``all_reduce(sum)`` of the cross-expert sum S and one
-``all_gather`` of the per-rank forecasts — run through ``torch.distributed`` on whatever device
-the buffers live on (NCCL over NVLink on the GPUs; gloo in the CPU tests).  The three compute
+gather of the per-rank forecasts — run through ``torch.distributed`` on whatever device
+the buffers live on (NCCL over NVLink on the GPUs; gloo in the CPU tests); on CUDA the gather goes
+over peer-mapped memory instead when it is available (K2 peer stores or DMA-engine 2-D copies).  The three compute
 phases are callables so the same orchestration is exercised by ``tests/test_sharding_gloo.py``
 without a GPU (there the callables are oracle code; in the product they are the C-ABI phases
 ``dr_forward_local_dev`` / ``dr_forward_heads_dev`` / ``dr_interleave_dev``).
