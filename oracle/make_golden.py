@@ -220,7 +220,94 @@ def featurize_golden():
     print("g9_featurize:", {k: (len(v["keys"]), len(v["raw"])) for k, v in out.items()})
 
 
+def synthesizer_golden():
+    """G11 — the trace synthesizer (synthesizer.py:10-52) run on synthetic buckets and on the shipped sample.
+    The reference's synthesize() uses the removed alias np.int; it is restored for the run (np.int = int)."""
+    import json
+    import pickle
+    import synthesizer as ref_syn                      # the reference module (script part is under __main__)
+    if not hasattr(np, "int"):
+        np.int = int
+    cases = {"synthetic": synthetic_buckets(123)}
+    with open("/root/reference/resource-estimation/raw_data.pkl", "rb") as f:
+        cases["shipped_sample"] = pickle.load(f)
+    out = {}
+    for name, raw in cases.items():
+        ref = ref_syn.TraceSynthesizer().fit(raw)
+        apis = list(ref.api2dist)
+        dist = {api: {"candidates": [eval(c) for c in ref.api2dist[api][0]], "weights": list(ref.api2dist[api][1])} for api in apis}
+        requests, vectors = [], []
+        for k in range(6):
+            u = synth.uniform(900 + k, 2 * len(apis))
+            req = {api: int(u[2 * i] * 9) for i, api in enumerate(apis) if u[2 * i + 1] < 0.8 or i == 0}
+            np.random.seed(4242 + k)
+            vectors.append([int(v) for v in ref.synthesize(req)])
+            requests.append(req)
+        out[name] = {"raw": raw, "keys": list(ref.M.keys()), "api2dist": dist, "seed0": 4242, "requests": requests, "vectors": vectors}
+    with open(os.path.join(OUT, "g11_synthesizer.json"), "w") as f:
+        json.dump(out, f)
+    print("g11_synthesizer:", {k: (len(v["api2dist"]), len(v["requests"])) for k, v in out.items()})
+
+
+def evaluation_golden():
+    """G12 — the test stage of estimate.py:79-122 executed with the reference QuantileRNN, utils.sliding_window and
+    QuantileRNN.normalization_minmax on a synthetic series: per-window selection, clamp, de-normalisation, error
+    percentiles and the console lines.  (estimate.py itself cannot be imported — it is a script that needs matplotlib —
+    so its loop is re-typed here around the reference's own functions; the DataLoader is replaced by indexing.)"""
+    import json
+    from utils import sliding_window as ref_sliding_window
+    M, F, N, W, split_frac = 4, 16, 900, 60, 0.40
+    names = ["svc%d_%s" % (i // 2, ("cpu", "memory")[i % 2]) for i in range(M)]
+    traffic = np.floor(synth.uniform(77, N * F).reshape(N, F) * 40.0)
+    res = synth.uniform(78, N * M).reshape(N, M) * np.asarray([200.0, 3000.0, 50.0, 900.0]) + np.asarray([10.0, 500.0, 1.0, 100.0])
+    X = ref_sliding_window(traffic, W)
+    y = ref_sliding_window(res, W)
+    split = int(len(X) * split_frac)
+    X, xmin, xmax = QuantileRNN.normalization_minmax(X, split=split)
+    scales = []
+    for idx in range(M):
+        y_, mn, mx = QuantileRNN.normalization_minmax(y[:, :, [idx]], split=split)
+        y[:, :, [idx]] = y_
+        scales.append((float(mx - mn), float(mn)))
+    X_test, y_test = torch.Tensor(X[split:]), torch.Tensor(y[split:])
+    model, blob = build_model(M, F, "synth", 1.5)
+    model.eval()
+    yerr = [[] for _ in names]
+    losses, lines = [], []
+    with torch.no_grad():
+        num_cycles = 0
+        for iv in range(len(X_test)):
+            if iv % W != 0 or num_cycles >= 9:
+                continue
+            num_cycles += 1
+            inputs, labels = X_test[iv:iv + 1], y_test[iv:iv + 1]
+            outputs = model(inputs)
+            losses.append(model.quantile_loss(outputs, labels).item())
+            labels = labels.numpy()[0]
+            outputs_deeprest = np.maximum(outputs.numpy(), 1e-6)[0]
+            for idx in range(M):
+                labels_ = labels[:, idx] * scales[idx][0] + scales[idx][1]
+                outputs_ = outputs_deeprest[:, idx, 1] * scales[idx][0] + scales[idx][1]
+                yerr[idx] += list(np.abs(outputs_ - labels_))
+    for idx, name in enumerate(names):
+        lines.append('===== %s =====' % name)
+        lines.append('   DEEPR => Median: %.4f | 95-th: %.4f | 99-th: %.4f | Max: %.4f' % (
+            float(np.median(yerr[idx])), np.percentile(yerr[idx], q=95), np.percentile(yerr[idx], q=99), np.max(yerr[idx])))
+    out = {"M": M, "F": F, "N": N, "W": W, "split": split, "names": names, "wseed": WSEED, "wscale": 1.5,
+           "traffic_seed": 77, "res_seed": 78, "xmin": float(xmin), "xmax": float(xmax), "scales": scales,
+           "loss": float(np.mean(losses)), "n_windows": num_cycles,
+           "summary": {n: [float(np.median(e)), float(np.percentile(e, 95)), float(np.percentile(e, 99)), float(np.max(e))]
+                       for n, e in zip(names, yerr)},
+           "lines": lines}
+    with open(os.path.join(OUT, "g12_evaluation.json"), "w") as f:
+        json.dump(out, f)
+    print("g12_evaluation:", num_cycles, "windows, loss", out["loss"])
+    print("\n".join(lines[:4]))
+
+
 if __name__ == "__main__":
     main()
+    evaluation_golden()
     featurize_golden()
     trained_golden()
+    synthesizer_golden()
