@@ -128,6 +128,8 @@ bool dr_tc_built();
 bool dr_tc_supported(const dr_model* m, int B, int T);
 int dr_tc_prep_weights(dr_model* m);
 int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev, float* out_local_dev);
+// training forward of one micro-batch on the tensor-core engine: saves (r,z,n), q, h per step in dr_train.cu's layout
+int dr_launch_gru_tc_train(dr_model* m, const float* x_dev, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows);
 // dr_train.cu
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);

@@ -70,7 +70,13 @@ __device__ __forceinline__ void store_bhn(uint32_t taddr, const float* src) {
     tmem_st8(taddr + 8, v1);
 }
 
-template <bool kTiming>
+// Training-mode outputs (kTrain): instead of reducing h into S and emitting head partials, the epilogue saves what the
+// backward pass of csrc/dr_train.cu consumes, in its layout: row = (e*T + t)*B + b (B = the micro-batch of this launch),
+//   rzn[dir][row][3H] = (r, z, n)    q[dir][row][H] = W_hn h_{t-1} + b_hn    hs[dir][row][H] = h_t
+// with dir_stride_rows rows between the two directions.  Dropout, S and the heads are applied by the training kernels.
+struct TcTrainOut { float* rzn; float* q; float* hs; long long dir_stride_rows; };
+
+template <bool kTiming, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][kWBytes]
                  const uint8_t* __restrict__ xtc,     // [T][ntiles][2 cta][hi|lo][kXTile]
@@ -79,7 +85,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                  float* __restrict__ S,               // [T][64][Bp][4]
                  float* __restrict__ P,               // own-expert head partials [T][Bp/128][ceil(3M_loc/16)][dir*2+half][16][128]
                  int B, int T, int Bp, int M_loc, int ntiles,
-                 unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */) {
+                 unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */,
+                 TcTrainOut tr /* used only when kTrain */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta = cluster_ctarank();
@@ -218,6 +225,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
             const int tt = dir ? (T - 1 - s) : s;
             const int tt_prev = dir ? (T - s) : (s - 1);
             const uint32_t hnext = (s & 1) ? kHA : kHB;           // step s reads (s&1 ? HB : HA), writes the other
+            // training mode: this thread's row of the saved activations for step tt
+            const size_t trow = kTrain ? (size_t)dir * (size_t)tr.dir_stride_rows + ((size_t)e * T + tt) * (size_t)B + (size_t)(live ? b : 0) : 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int buf = q & 1;
@@ -241,7 +250,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     if (lane == 0) mbar_arrive_remote(bar(GATE_FREE0 + buf), 0);
                 }
                 const long long tq2 = timing ? clock64() : 0;
-                if (half == 1 && (s > 0 || q > 0)) {              // lagging warp: previous quarter's tail first
+                if (!kTrain && half == 1 && (s > 0 || q > 0)) {   // lagging warp: previous quarter's tail first
                     tail(((q + 3) & 3) * 32 + 16, q == 0 ? tt_prev : tt);
                     if (q == 0) flush(tt_prev);
                 }
@@ -277,10 +286,13 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     for (int i = 0; i < 4; ++i) iv2[i] = rcp_approx(rr[2 * i] * rr[2 * i + 1]);
                     // n = tanh(gi_n + b_in + r*(gh_n + b_hn)) = 1 - 2/(1 + exp(2t));  b_hn is already in gh
 #pragma unroll
+                    float rv[8], nv[8];                                       // kept only by the training variant
+#pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float inv = rr[i ^ 1] * iv2[i >> 1];          // 1/((1+er_i)(1+ez_i))
                         zz[i] = er[i] * inv;
                         const float r_i = ez[i] * inv;
+                        rv[i] = r_i;
                         const float t = fmaf(r_i, __uint_as_float(gh[j8 + i]), __uint_as_float(gi[j8 + i]));
                         pn[i] = fminf(fmaf(t, 2.0f * kLog2e, cn[i]), 30.0f);
                     }
@@ -306,12 +318,27 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         const float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
                         hreg[q][j] = a0; hreg[q][j + 1] = a1;
                         hn[j] = a0; hn[j + 1] = a1;
+                        nv[i] = n0; nv[i + 1] = n1;
                         // fp16 split of the pair with packed conversions (F2FP / HADD2.F32: no XU-pipe traffic)
                         __half2 hi2 = __floats2half2_rn(a0, a1);
                         float2 back = __half22float2(hi2);
                         __half2 lo2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
                         phi[j >> 1] = *reinterpret_cast<uint32_t*>(&hi2);
                         plo[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
+                    }
+                    if (kTrain && live) {
+                        float* pr = tr.rzn + trow * (3 * DR_H) + u0 + j8;
+                        float* pq = tr.q + trow * DR_H + u0 + j8;
+                        float* ph = tr.hs + trow * DR_H + u0 + j8;
+#pragma unroll
+                        for (int v = 0; v < 8; v += 4) {
+                            *reinterpret_cast<float4*>(pr + v) = make_float4(rv[v], rv[v + 1], rv[v + 2], rv[v + 3]);
+                            *reinterpret_cast<float4*>(pr + DR_H + v) = make_float4(zz[v], zz[v + 1], zz[v + 2], zz[v + 3]);
+                            *reinterpret_cast<float4*>(pr + 2 * DR_H + v) = make_float4(nv[v], nv[v + 1], nv[v + 2], nv[v + 3]);
+                            *reinterpret_cast<float4*>(pq + v) = make_float4(__uint_as_float(gh[j8 + v]), __uint_as_float(gh[j8 + v + 1]),
+                                                                             __uint_as_float(gh[j8 + v + 2]), __uint_as_float(gh[j8 + v + 3]));
+                            *reinterpret_cast<float4*>(ph + v) = make_float4(hn[j8 + v], hn[j8 + v + 1], hn[j8 + v + 2], hn[j8 + v + 3]);
+                        }
                     }
                 }
                 tmem_st8(tbase + lane_base + hnext + u0 / 2, phi);
@@ -321,14 +348,14 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(bar(H_READY0 + q), 0);   // K columns [32q, 32q+32) of h_t are in TMEM
                 const long long tq3 = timing ? clock64() : 0;
-                if (half == 0) { tail(u0, tt); if (q == 3) flush(tt); }
+                if (!kTrain && half == 0) { tail(u0, tt); if (q == 3) flush(tt); }
                 if (timing) {
                     const long long tq4 = clock64();
                     t_wait[q] += tq1 - tq0; t_ld += tq2 - tq1; t_math += tq3 - tq2; t_tail += tq4 - tq3;
                 }
             }
         }
-        if (half == 1) { const int tl = dir ? 0 : (T - 1); tail(3 * 32 + 16, tl); flush(tl); }
+        if (!kTrain && half == 1) { const int tl = dir ? 0 : (T - 1); tail(3 * 32 + 16, tl); flush(tl); }
         if (timing) {
             dbg[0] = (unsigned long long)(clock64() - t_begin);
             for (int q = 0; q < 4; ++q) dbg[1 + q] = (unsigned long long)t_wait[q];
@@ -561,21 +588,46 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
                                                            m->x_bstride ? m->x_bstride : (long long)T * m->cfg.F);
         DR_CUDA(m, cudaGetLastError());
     }
-    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     int items = m->M_loc * 2 * ntiles;
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
     if (m->d_tc_dbg)
-        dr_gru_tc_kernel<true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+        dr_gru_tc_kernel<true, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg);
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg, TcTrainOut{});
     else
-        dr_gru_tc_kernel<false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+        dr_gru_tc_kernel<false, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr);
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{});
     DR_CUDA(m, cudaGetLastError());
     if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
+    m->launches += 2;
+    return DR_OK;
+}
+
+// Training forward of one micro-batch on the tensor-core engine: the same recurrence kernel, instantiated to save the
+// per-step activations (r, z, n, q, h) the backward pass needs instead of producing S and head partials (the training
+// kernels apply dropout, the cross-expert sum and the heads from hs).  x points at the first window of the micro-batch.
+int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows) {
+    if (m->M_loc == 0 || Bm <= 0 || T <= 0) return DR_OK;
+    const int ntiles = (Bm + 255) / 256, Bp = (Bm + 127) / 128 * 128;
+    const size_t xbytes = (size_t)T * ntiles * 2 * kXStage;
+    int rc = dr_reserve(m, &m->d_xtc, &m->xtc_cap, xbytes);
+    if (rc != DR_OK) return rc;
+    {
+        size_t total = (size_t)T * ntiles * 256 * 8;
+        dr_tc_pack_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), Bm, T, m->cfg.F,
+                                                                                    ntiles, (long long)T * m->cfg.F);
+        DR_CUDA(m, cudaGetLastError());
+    }
+    DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    const int items = m->M_loc * 2 * ntiles;
+    dr_gru_tc_kernel<false, true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
+        reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
+        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows});
+    DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
     return DR_OK;
 }

@@ -438,7 +438,18 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     if (m->cfg.dropout_p >= 1.0f) return dr_fail(m, DR_EINVAL, "dropout_p must be < 1");
     // micro-batch size from a memory budget (4.5 KB per expert-window-step-direction, see header)
     size_t per_window = (size_t)2 * Ml * T * (3 * DR_H * 2 + DR_H * 3) * sizeof(float);
+    // budget: half of the HBM that is free right now plus what this workspace already holds, at least 8 GB (a 180 GB
+    // B200 gives ~85 GB: config-2-sized micro-batches of 256+ windows stay in one piece, so nothing is recomputed and
+    // the per-step GEMMs of the backward chain run on full 128-row tiles)
     size_t budget = (size_t)24 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            const dr_train_ws* cur = reinterpret_cast<const dr_train_ws*>(m->train_ws);
+            size_t held = cur ? (size_t)2 * Ml * cur->cap_rows * (3 * DR_H * 2 + DR_H * 3) * sizeof(float) : 0;
+            budget = std::max<size_t>((size_t)8 << 30, (free_b + held) / 2);
+        }
+    }
     int Bm = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, budget / std::max<size_t>(per_window, 1)));
     if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) Bm = std::min(B, v); }   // test hook
     dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
@@ -482,7 +493,14 @@ static int train_forward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     const size_t r = (size_t)T * bm;
     const size_t ed_stride = (size_t)Ml * ws->cap_rows;
     dr_time_major_kernel<<<nblk(r * F), 256, 0, st>>>(ws->x, ws->xt, b0, bm, T, F);
-    for (int d = 0; d < 2; ++d) {
+    // Tensor-core engine: the whole recurrence of the micro-batch (both directions, all experts) is ONE launch of the
+    // tcgen05 kernel of the inference path, instantiated to save (r,z,n), q and h per step (csrc/dr_gru_tc.cu).
+    const bool tc_fwd = m->cfg.engine != DR_ENGINE_FFMA && dr_tc_supported(m, bm, T) && m->d_wtc != nullptr;
+    if (tc_fwd) {
+        int rc = dr_launch_gru_tc_train(m, ws->x + (size_t)b0 * T * F, bm, T, ws->rzn, ws->q, ws->hs, (long long)ed_stride);
+        if (rc) return rc;
+    }
+    for (int d = 0; d < 2 && !tc_fwd; ++d) {
         float* gi = ws->gi + d * ed_stride * 3 * DR_H;
         float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
         float* q = ws->q + d * ed_stride * DR_H;
@@ -512,7 +530,8 @@ static int train_forward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     size_t ts = r * DR_2H;
     dr_sum_experts_kernel<<<nblk(ts), 256, 0, st>>>(ws->hs, ws->hs + ed_stride * DR_H, ws->mask, ws->seed, p, ws->S, Ml, m->e_lo, B, b0, bm, T, ts);
     DR_CUDA(m, cudaGetLastError());
-    m->launches += 2 + 2 * (2 + 2 * T);
+    m->launches += tc_fwd ? 2 : 2 + 2 * (2 + 2 * T);
+    m->last_engine = tc_fwd ? "tcgen05" : "ffma";
     return DR_OK;
 }
 

@@ -13,40 +13,59 @@ from oracle import qrnn_numpy as oracle
 pytestmark = pytest.mark.gpu
 
 
-def check_grads(got, ref, F, tag):
+ENGINES = ["auto", "ffma"]       # auto: forward recurrence on the tcgen05 kernel (split-fp16, approx gates); ffma: exact fp32
+
+
+def check_grads(got, ref, F, tag, engine="ffma", rows=1):
     scale = np.abs(ref).max()
-    assert np.abs(got - ref).max() <= 5e-6 * scale + 1e-9, f"{tag}: max grad err {np.abs(got - ref).max():.3e} (scale {scale:.3e})"
+    # the tensor-core forward saves activations that differ from exact fp32 by ~1e-7 relative (same arithmetic as the
+    # inference engine, whose outputs meet the 1e-6 + 1e-4|ref| bar); the gradient bound is doubled for it.  Every
+    # gradient is an fp32 reduction over the B*T rows in a different order than the oracle's: the bound grows with
+    # sqrt(rows) beyond the ~100 rows of the small cases.
+    overall = (5e-6 if engine == "ffma" else 1e-5) * max(1.0, (rows / 100.0) ** 0.5)
+    assert np.abs(got - ref).max() <= overall * scale + 1e-9, f"{tag}: max grad err {np.abs(got - ref).max():.3e} (scale {scale:.3e})"
     pe = layout.params_per_expert(F)
     for name, (off, shape) in layout.expert_offsets(F).items():
         n = int(np.prod(shape))
         for e in range(got.size // pe):
             a, b = got[e * pe + off:e * pe + off + n], ref[e * pe + off:e * pe + off + n]
-            tol = 2e-5 * max(np.abs(b).max(), 1e-7) + 1e-9
+            tol = 2e-5 * max(1.0, (rows / 100.0) ** 0.5) * max(np.abs(b).max(), 1e-7) + 1e-9
             assert np.abs(a - b).max() <= tol, f"{tag}: {name}[expert {e}] err {np.abs(a - b).max():.3e} vs max {np.abs(b).max():.3e}"
 
 
-def test_train_step_matches_reference_golden():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_train_step_matches_reference_golden(engine):
     g = dict(np.load(os.path.join(GOLDEN_DIR, "g5_train_step.npz")))
     M, B, T, F = (int(g[k]) for k in ("M", "B", "T", "F"))
     blob = synth.weights(int(g["wseed"]), M, F, float(g["wscale"]))
     x = synth.windows(int(g["xseed"]), B, T, F, str(g["xkind"]))
     y = synth.labels(int(g["yseed"]), B, T, M)
     dm = (synth.uniform(int(g["mask_seed"]), M * B * T * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(M, B, T, 2 * layout.H)
-    m = QuantileRNN(F, M)
+    m = QuantileRNN(F, M, engine=engine)
     try:
         m.load_blob(blob)
         loss = m.train_step(x, y, lr=float(g["lr"]), dropout_mask=dm)
+        assert m.last_engine == ("ffma" if engine == "ffma" else "tcgen05")     # the forward recurrence really ran there
         grads = m.grads()
         after = m.blob()
     finally:
         m.close()
     assert abs(loss - float(g["loss"])) < 2e-6
-    check_grads(grads, g["grads"], F, "vs reference autograd")
-    assert np.abs(after - g["weights_after"]).max() < 2e-6, np.abs(after - g["weights_after"]).max()
+    check_grads(grads, g["grads"], F, "vs reference autograd", engine, rows=B * T)
+    if engine == "ffma":
+        assert np.abs(after - g["weights_after"]).max() < 2e-6, np.abs(after - g["weights_after"]).max()
+    else:
+        # Adam's first step moves a weight by lr*g/(|g|+eps): where |g| ~ eps a 1e-9 gradient difference legitimately changes
+        # the update, so the tensor-core variant is checked on its own gradients (torch's Adam arithmetic, oracle.adam_step)
+        ref_w, _, _ = oracle.adam_step(blob, grads, np.zeros_like(blob), np.zeros_like(blob), step=1, lr=float(g["lr"]))
+        assert np.abs(after - ref_w).max() <= 3e-7 * max(1.0, np.abs(ref_w).max())
+        big = np.abs(g["grads"]) > 1e-3 * np.abs(g["grads"]).max()        # and directly where the gradient is not tiny
+        assert np.abs(after - g["weights_after"])[big].max() < 2e-6
 
 
-@pytest.mark.parametrize("M,B,T,F,mb", [(3, 5, 7, 5, 0), (2, 9, 4, 16, 4), (4, 6, 12, 33, 0)])
-def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("M,B,T,F,mb", [(3, 5, 7, 5, 0), (2, 9, 4, 16, 4), (4, 6, 12, 33, 0), (2, 300, 5, 16, 0), (2, 300, 3, 8, 140)])
+def test_train_step_matches_oracle(M, B, T, F, mb, engine, monkeypatch):
     if mb:
         monkeypatch.setenv("DR_TRAIN_MICROBATCH", str(mb))        # force the multi-micro-batch path
     blob = synth.weights(40 + M, M, F, 1.5)
@@ -54,7 +73,7 @@ def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
     y = synth.labels(4, B, T, M)
     dm = (synth.uniform(8, M * B * T * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(M, B, T, 2 * layout.H)
     ref_loss, _, ref_g = oracle.loss_and_grads(blob, x, y, M, F, dropout_masks=dm.astype(np.float32))
-    m = QuantileRNN(F, M)
+    m = QuantileRNN(F, M, engine=engine)
     try:
         m.load_blob(blob)
         loss = m.train_step(x, y, lr=1e-3, dropout_mask=dm)
@@ -65,7 +84,7 @@ def test_train_step_matches_oracle(M, B, T, F, mb, monkeypatch):
     finally:
         m.close()
     assert abs(loss - float(ref_loss)) < 2e-6
-    check_grads(grads, ref_g, F, "vs oracle")
+    check_grads(grads, ref_g, F, "vs oracle", engine, rows=B * T)
     # Adam is checked on the GPU's own gradients: at step 1 the update is lr*g/(|g|+eps), so where |g| ~ eps a
     # 1e-9 gradient difference legitimately moves the weight by more than any fixed tolerance
     ref_w, _, _ = oracle.adam_step(blob, grads, np.zeros_like(blob), np.zeros_like(blob), step=1)
