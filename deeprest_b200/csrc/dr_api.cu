@@ -87,6 +87,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
     for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; }
     m->d_p = nullptr; m->p_cap = 0; m->p_live = false; m->d_himg = nullptr;
+    m->d_xtc_tr = nullptr; m->xtc_tr_cap = 0; m->d_whT = nullptr; m->whT_cap = 0;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
     m->d_xin = nullptr; m->xin_cap = 0; m->d_loss = nullptr; m->d_y = nullptr; m->y_cap = 0;
 
@@ -119,7 +120,7 @@ void dr_destroy(dr_model* m) {
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
-    void* ptrs[] = {m->d_himg, m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
+    void* ptrs[] = {m->d_xtc_tr, m->d_whT, m->d_himg, m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->ws_S[0], m->ws_S[1], m->ws_S[2], m->ws_S[3], m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);

@@ -71,6 +71,8 @@ struct dr_model {
     float* d_p; size_t p_cap; bool p_live;   // own-expert head partials of the call being issued / consumed (tcgen05 engine)
     float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
     void*  d_xtc;  size_t xtc_cap;  // x split to bf16 hi/lo [T, Bp, Fp]      (tcgen05 engine)
+    void*  d_xtc_tr; size_t xtc_tr_cap;   // x image of the training micro-batch (own buffer: d_xtc above aliases a ring slot)
+    void*  d_whT;    size_t whT_cap;      // W_hh^T split-fp16 images for the tensor-core backward recurrence (dr_gru_bwd_tc.cu)
     float* d_S;    size_t S_cap;    // [T][2H/4][Bp][4]
     float* d_out;  size_t out_cap;  // staging for host entry points
     float* d_xin;  size_t xin_cap;  // staging for host entry points
@@ -130,6 +132,9 @@ int dr_tc_prep_weights(dr_model* m);
 int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev, float* out_local_dev);
 // training forward of one micro-batch on the tensor-core engine: saves (r,z,n), q, h per step in dr_train.cu's layout
 int dr_launch_gru_tc_train(dr_model* m, const float* x_dev, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows);
+// backward recurrence of one micro-batch on the tensor-core engine (dr_gru_bwd_tc.cu): gate adjoints + dh chain, in place
+int dr_launch_gru_bwd_tc(dr_model* m, float* rzn, float* gi, const float* q, const float* hs, const float* dhout,
+                         long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n);
 // dr_train.cu
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);

@@ -614,18 +614,18 @@ int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rz
     if (m->M_loc == 0 || Bm <= 0 || T <= 0) return DR_OK;
     const int ntiles = (Bm + 255) / 256, Bp = (Bm + 127) / 128 * 128;
     const size_t xbytes = (size_t)T * ntiles * 2 * kXStage;
-    int rc = dr_reserve(m, &m->d_xtc, &m->xtc_cap, xbytes);
+    int rc = dr_reserve(m, &m->d_xtc_tr, &m->xtc_tr_cap, xbytes);      // not m->d_xtc: that one aliases a slot of the forward ring
     if (rc != DR_OK) return rc;
     {
         size_t total = (size_t)T * ntiles * 256 * 8;
-        dr_tc_pack_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc), Bm, T, m->cfg.F,
+        dr_tc_pack_x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, m->stream>>>(x, reinterpret_cast<uint8_t*>(m->d_xtc_tr), Bm, T, m->cfg.F,
                                                                                     ntiles, (long long)T * m->cfg.F);
         DR_CUDA(m, cudaGetLastError());
     }
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     const int items = m->M_loc * 2 * ntiles;
     dr_gru_tc_kernel<false, true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
-        reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
+        reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc_tr), m->d_bias4, m->d_ct,
         nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows});
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;

@@ -553,14 +553,22 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     }
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
+    // Tensor-core engine: the reverse-time chain (gate adjoints + dh_{t-1} = dh*z + dgh W_hh) of both directions and all
+    // experts is ONE persistent tcgen05 kernel (csrc/dr_gru_bwd_tc.cu) instead of 2(T-1) x {gate kernel, fp32 GEMM}.
+    const bool tc_bwd = m->cfg.engine != DR_ENGINE_FFMA && Ml > 0;
+    if (tc_bwd) {
+        int rc = dr_launch_gru_bwd_tc(m, ws->rzn, ws->gi, ws->q, ws->hs, ws->dhout, (long long)ed_stride, (long long)((size_t)Ml * r), bm, T,
+                                      1.0f / ((float)M * (float)B * (float)T));
+        if (rc) return rc;
+    }
     for (int d = 0; d < 2 && Ml; ++d) {
         float* gi = ws->gi + d * ed_stride * 3 * DR_H;
         float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
         float* q = ws->q + d * ed_stride * DR_H;
         float* hs = ws->hs + d * ed_stride * DR_H;
         float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
-        DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
-        for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
+        if (!tc_bwd) DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
+        for (int s = T - 1; s >= 0 && !tc_bwd; --s) {           // reverse of the forward processing order
             const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
             const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
             size_t tg = (size_t)Ml * bm * DR_H;
@@ -592,7 +600,7 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
         dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);
         dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(gi, m->d_grad, m->off.b_ih[d], pe, r, chunk);
         DR_CUDA(m, cudaGetLastError());
-        m->launches += 3 + 2 * T;
+        m->launches += tc_bwd ? 5 : 3 + 2 * T;
     }
     return DR_OK;
 }

@@ -13,7 +13,7 @@ from oracle import qrnn_numpy as oracle
 pytestmark = pytest.mark.gpu
 
 
-ENGINES = ["auto", "ffma"]       # auto: forward recurrence on the tcgen05 kernel (split-fp16, approx gates); ffma: exact fp32
+ENGINES = ["auto", "ffma"]       # auto: forward and backward recurrences on the tcgen05 kernels (split-fp16); ffma: exact fp32
 
 
 def check_grads(got, ref, F, tag, engine="ffma", rows=1):
@@ -45,7 +45,7 @@ def test_train_step_matches_reference_golden(engine):
     try:
         m.load_blob(blob)
         loss = m.train_step(x, y, lr=float(g["lr"]), dropout_mask=dm)
-        assert m.last_engine == ("ffma" if engine == "ffma" else "tcgen05")     # the forward recurrence really ran there
+        assert m.last_engine == ("ffma" if engine == "ffma" else "tcgen05")     # the recurrences really ran there
         grads = m.grads()
         after = m.blob()
     finally:
@@ -64,7 +64,7 @@ def test_train_step_matches_reference_golden(engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("M,B,T,F,mb", [(3, 5, 7, 5, 0), (2, 9, 4, 16, 4), (4, 6, 12, 33, 0), (2, 300, 5, 16, 0), (2, 300, 3, 8, 140)])
+@pytest.mark.parametrize("M,B,T,F,mb", [(3, 5, 7, 5, 0), (2, 9, 4, 16, 4), (4, 6, 12, 33, 0), (2, 300, 5, 16, 0), (2, 300, 3, 8, 140), (2, 3, 4, 70, 0)])
 def test_train_step_matches_oracle(M, B, T, F, mb, engine, monkeypatch):
     if mb:
         monkeypatch.setenv("DR_TRAIN_MICROBATCH", str(mb))        # force the multi-micro-batch path
