@@ -275,9 +275,7 @@ int dr_launch_gru_bwd_tc(dr_model* m, float* rzn, float* gi, const float* q, con
     }
     // dgh ~ dL/dy ~ inv_n = 1/(M*B*T): scale by 2^ka with 2^ka * inv_n in [4, 8) — fp16 keeps 4 decades of head room above
     // and the hi/lo split 3 decades below before the lo part goes subnormal
-    int ex = 0;
-    frexpf(inv_n, &ex);                                   // inv_n = f * 2^ex, f in [0.5, 1)
-    const int ka = 3 - ex;
+    const int ka = dr_grad_scale_log2(inv_n);
     BwdArgs a;
     a.wimg = reinterpret_cast<const uint8_t*>(m->d_whT);
     a.rzn = rzn; a.gi = gi; a.q = q; a.hs = hs; a.dhout = dhout;

@@ -556,6 +556,7 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     // Tensor-core engine: the reverse-time chain (gate adjoints + dh_{t-1} = dh*z + dgh W_hh) of both directions and all
     // experts is ONE persistent tcgen05 kernel (csrc/dr_gru_bwd_tc.cu) instead of 2(T-1) x {gate kernel, fp32 GEMM}.
     const bool tc_bwd = m->cfg.engine != DR_ENGINE_FFMA && Ml > 0;
+    const bool tc_wgrad = tc_bwd && getenv("DR_TRAIN_WGRAD_FFMA") == nullptr;      // escape hatch: keep the fp32 GEMMs
     if (tc_bwd) {
         int rc = dr_launch_gru_bwd_tc(m, ws->rzn, ws->gi, ws->q, ws->hs, ws->dhout, (long long)ed_stride, (long long)((size_t)Ml * r), bm, T,
                                       1.0f / ((float)M * (float)B * (float)T));
@@ -584,15 +585,30 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
         const size_t skip = (size_t)bm;
         const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
         const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
+        // the two reductions over all (t,b) rows: fp32 CUDA-core GEMM, or split-fp16 tcgen05 (csrc/dr_wgrad_tc.cu) with the
+        // gradient operand scaled by the same power of two as in the recurrence kernel and h / x by 2^4
+        const int ka = dr_grad_scale_log2(1.0f / ((float)M * (float)B * (float)T));
         if (T > 1) {
-            Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
-                    1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
-            int rc = gemm(m, gw, Ml);
-            if (rc) return rc;
+            if (tc_wgrad) {
+                int rc = dr_launch_wgrad_tc(m, A, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bp, DR_H, (long long)T * bm * DR_H,
+                                            m->d_grad + m->off.w_hh[d], DR_H, (long long)pe, 3 * DR_H, DR_H, (int)(r - skip), Ml, ka, 4, 1);
+                if (rc) return rc;
+            } else {
+                Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
+                        1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
+                int rc = gemm(m, gw, Ml);
+                if (rc) return rc;
+            }
         }
-        Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
-                (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
-        int rc = gemm(m, gp, Ml);
+        int rc;
+        if (tc_wgrad && dr_wgrad_tc_ok(3 * DR_H, F, (int)r)) {
+            rc = dr_launch_wgrad_tc(m, gi, 3 * DR_H, (long long)T * bm * 3 * DR_H, ws->xt, F, 0, ws->P, F, (long long)3 * DR_H * F,
+                                    3 * DR_H, F, (int)r, Ml, ka, 4, 0);
+        } else {
+            Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
+                    (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
+            rc = gemm(m, gp, Ml);
+        }
         if (rc) return rc;
         dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
         int chunk = 1024;
