@@ -260,18 +260,26 @@ __global__ void dr_gbar_kernel(const float* __restrict__ dy, const float* __rest
 __global__ void dr_dhout_kernel(const float* __restrict__ dy, const float* __restrict__ gbar, const float* __restrict__ ct,
                                 const uint8_t* __restrict__ mask, uint64_t seed, float p, float* __restrict__ dhout,
                                 int M_loc, int e_lo, int B, int b0, int Bm, int T, size_t total) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int j = (int)(i % DR_H); size_t r = i / DR_H;
+    size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // one thread = 4 consecutive hidden units
+    if (i4 * 4 >= total) return;
+    int j = (int)(i4 % (DR_H / 4)) * 4; size_t r = i4 / (DR_H / 4);
     int b = (int)(r % Bm); r /= Bm;
     int t = (int)(r % T); r /= T;
     int e = (int)(r % M_loc); int d = (int)(r / M_loc);
     int k = d * DR_H + j;
     const float* dd = dy + (((size_t)(b0 + b) * T + t) * M_loc + e) * DR_Q;
     const float* c = ct + ((size_t)(e * 2 + d) * DR_Q) * DR_H + j;
-    float v = c[0] * dd[0] + c[DR_H] * dd[1] + c[2 * DR_H] * dd[2] + gbar[((size_t)t * Bm + b) * DR_2H + k];
-    size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
-    dhout[i] = v * keep_scale(mask, seed, midx, p, 1.0f / (1.0f - p));
+    const float d0 = dd[0], d1 = dd[1], d2 = dd[2];
+    const float4 c0 = *reinterpret_cast<const float4*>(c), c1 = *reinterpret_cast<const float4*>(c + DR_H), c2 = *reinterpret_cast<const float4*>(c + 2 * DR_H);
+    const float4 gb = *reinterpret_cast<const float4*>(gbar + ((size_t)t * Bm + b) * DR_2H + k);
+    const size_t midx = (((size_t)(e_lo + e) * B + b0 + b) * T + t) * DR_2H + k;
+    const float ik = 1.0f / (1.0f - p);
+    float4 o;                                                            // same operation order per element as before
+    o.x = (c0.x * d0 + c1.x * d1 + c2.x * d2 + gb.x) * keep_scale(mask, seed, midx, p, ik);
+    o.y = (c0.y * d0 + c1.y * d1 + c2.y * d2 + gb.y) * keep_scale(mask, seed, midx + 1, p, ik);
+    o.z = (c0.z * d0 + c1.z * d1 + c2.z * d2 + gb.z) * keep_scale(mask, seed, midx + 2, p, ik);
+    o.w = (c0.w * d0 + c1.w * d1 + c2.w * d2 + gb.w) * keep_scale(mask, seed, midx + 3, p, ik);
+    *reinterpret_cast<float4*>(dhout + i4 * 4) = o;
 }
 
 // head weight gradients: U[e][q][k] = sum_{t,b} dy r~ ; V = sum dy S ; db = sum dy.   grid (M_loc, chunks), 256 threads = k
@@ -463,7 +471,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
             (rc = ws_alloc(m, &ws->hs, E2 * rows * DR_H)) || (rc = ws_alloc(m, &ws->dhout, E2 * rows * DR_H)) ||
             (rc = ws_alloc(m, &ws->gh, (size_t)Ml * Bm * 3 * DR_H)) || (rc = ws_alloc(m, &ws->dhc, (size_t)Ml * Bm * DR_H)) ||
             (rc = ws_alloc(m, &ws->S, rows * DR_2H)) || (rc = ws_alloc(m, &ws->gbar, rows * DR_2H)) ||
-            (rc = ws_alloc(m, &ws->dy, (size_t)B * T * Ml * DR_Q)) || (rc = ws_alloc(m, &ws->P, (size_t)Ml * 3 * DR_H * F)) ||
+            (rc = ws_alloc(m, &ws->dy, (size_t)B * T * Ml * DR_Q)) || (rc = ws_alloc(m, &ws->P, (size_t)2 * Ml * 3 * DR_H * F)) ||
             (rc = ws_alloc(m, &ws->dmask, (size_t)Ml * F)))
             return rc;
         ws->cap_rows = rows; ws->cap_B = B; ws->cap_T = T;
@@ -544,7 +552,7 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     const size_t ed_stride = (size_t)Ml * ws->cap_rows;
     size_t td = (size_t)2 * Ml * r * DR_H;
     // dhout is laid out [d][e][(t,b)][H] with the (t,b) row stride of this micro-batch
-    if (td) dr_dhout_kernel<<<nblk(td), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, ws->mask, ws->seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
+    if (td) dr_dhout_kernel<<<nblk(td / 4), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, ws->mask, ws->seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
     if (Ml) {
         int chunk = 2048;
         dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
@@ -562,12 +570,40 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
                                       1.0f / ((float)M * (float)B * (float)T));
         if (rc) return rc;
     }
+    // weight gradients over all (t,b) rows of the micro-batch; dW_hh skips the step whose h_prev is the zero initial state.
+    // Tensor-core engine: split-fp16 tcgen05 reductions (csrc/dr_wgrad_tc.cu), both directions in one grid, the gradient
+    // operand scaled by the same power of two as in the recurrence kernel and h / x by 2^4.
+    const size_t skip = (size_t)bm;
+    const size_t p_dir = (size_t)Ml * 3 * DR_H * F;             // ws->P holds one [Ml][3H][F] block per direction
+    const bool p_tc = tc_wgrad && dr_wgrad_tc_ok(3 * DR_H, F, (int)r);
+    if (tc_wgrad) {
+        const int ka = dr_grad_scale_log2(1.0f / ((float)M * (float)B * (float)T));
+        const float *Aw[2], *Bw[2], *Ap[2], *Bx[2];
+        float *Cw[2], *Cp[2];
+        for (int d = 0; d < 2; ++d) {
+            Aw[d] = ws->rzn + d * ed_stride * 3 * DR_H + (d ? 0 : skip * 3 * DR_H);    // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
+            Bw[d] = ws->hs + d * ed_stride * DR_H + (d ? skip * DR_H : 0);              // h_{t-1} (fwd) / h_{t+1} (rev)
+            Cw[d] = m->d_grad + m->off.w_hh[d];
+            Ap[d] = ws->gi + d * ed_stride * 3 * DR_H; Bx[d] = ws->xt; Cp[d] = ws->P + d * p_dir;
+        }
+        if (T > 1) {
+            int rc = dr_launch_wgrad_tc(m, 2, Aw, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bw, DR_H, (long long)T * bm * DR_H, Cw, DR_H,
+                                        (long long)pe, 3 * DR_H, DR_H, (int)(r - skip), Ml, ka, 4, 1);
+            if (rc) return rc;
+        }
+        if (p_tc) {
+            int rc = dr_launch_wgrad_tc(m, 2, Ap, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bx, F, 0, Cp, F, (long long)3 * DR_H * F,
+                                        3 * DR_H, F, (int)r, Ml, ka, 4, 0);
+            if (rc) return rc;
+        }
+    }
     for (int d = 0; d < 2 && Ml; ++d) {
         float* gi = ws->gi + d * ed_stride * 3 * DR_H;
         float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
         float* q = ws->q + d * ed_stride * DR_H;
         float* hs = ws->hs + d * ed_stride * DR_H;
         float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
+        float* Pd = ws->P + (p_tc ? d * p_dir : 0);
         if (!tc_bwd) DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
         for (int s = T - 1; s >= 0 && !tc_bwd; --s) {           // reverse of the forward processing order
             const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
@@ -581,36 +617,21 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
                 if (rc) return rc;
             }
         }
-        // weight gradients over all (t,b) of the micro-batch; dW_hh skips the step whose h_prev is the zero initial state
-        const size_t skip = (size_t)bm;
-        const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
-        const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
-        // the two reductions over all (t,b) rows: fp32 CUDA-core GEMM, or split-fp16 tcgen05 (csrc/dr_wgrad_tc.cu) with the
-        // gradient operand scaled by the same power of two as in the recurrence kernel and h / x by 2^4
-        const int ka = dr_grad_scale_log2(1.0f / ((float)M * (float)B * (float)T));
-        if (T > 1) {
-            if (tc_wgrad) {
-                int rc = dr_launch_wgrad_tc(m, A, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bp, DR_H, (long long)T * bm * DR_H,
-                                            m->d_grad + m->off.w_hh[d], DR_H, (long long)pe, 3 * DR_H, DR_H, (int)(r - skip), Ml, ka, 4, 1);
-                if (rc) return rc;
-            } else {
-                Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
-                        1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
-                int rc = gemm(m, gw, Ml);
-                if (rc) return rc;
-            }
+        if (!tc_wgrad && T > 1) {
+            const float* A = rzn + (d ? 0 : skip * 3 * DR_H);
+            const float* Bp = hs + (d ? skip * DR_H : 0);
+            Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
+                    1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
+            int rc = gemm(m, gw, Ml);
+            if (rc) return rc;
         }
-        int rc;
-        if (tc_wgrad && dr_wgrad_tc_ok(3 * DR_H, F, (int)r)) {
-            rc = dr_launch_wgrad_tc(m, gi, 3 * DR_H, (long long)T * bm * 3 * DR_H, ws->xt, F, 0, ws->P, F, (long long)3 * DR_H * F,
-                                    3 * DR_H, F, (int)r, Ml, ka, 4, 0);
-        } else {
-            Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
+        if (!p_tc) {
+            Gemm gp{gi, ws->xt, Pd, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
                     (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
-            rc = gemm(m, gp, Ml);
+            int rc = gemm(m, gp, Ml);
+            if (rc) return rc;
         }
-        if (rc) return rc;
-        dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
+        dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(Pd, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
         int chunk = 1024;
         dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
         dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);

@@ -18,10 +18,10 @@ constexpr int kWgConv = 256;
 constexpr uint32_t kWgAPart = 128 * 128;              // A tile part: 128 rows (m) x 64 k fp16 = 16 KB
 enum WgBar { WG_FULL0 = 0, WG_FULL1, WG_EMPTY0, WG_EMPTY1, WG_DFULL, WG_NUM };
 
-struct WgArgs {
-    const float* A; long long lda, bsA;
-    const float* B; long long ldb, bsB;
-    float* C; long long ldc, bsC;
+struct WgArgs {                                       // blockIdx.z selects one of up to two problems (the two GRU directions)
+    const float* A[2]; long long lda, bsA;
+    const float* B[2]; long long ldb, bsB;
+    float* C[2]; long long ldc, bsC;
     int M, N, Npad, K;
     float a_scale, b_scale, c_unscale;
     int accumulate;
@@ -30,12 +30,14 @@ struct WgArgs {
 __device__ __forceinline__ void split8_store(const float (&v)[8], float scale, uint8_t* hi_dst, uint8_t* lo_dst) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        __half h0, l0, h1, l1;
-        split_f16(v[2 * j] * scale, h0, l0);
-        split_f16(v[2 * j + 1] * scale, h1, l1);
-        hi[j] = pack_h2(h0, h1);
-        lo[j] = pack_h2(l0, l1);
+    for (int j = 0; j < 4; ++j) {                       // packed conversions (F2FP): no XU-pipe traffic
+        const float a0 = fminf(fmaxf(v[2 * j] * scale, -65504.0f), 65504.0f);
+        const float a1 = fminf(fmaxf(v[2 * j + 1] * scale, -65504.0f), 65504.0f);
+        __half2 hi2 = __floats2half2_rn(a0, a1);
+        const float2 back = __half22float2(hi2);
+        __half2 lo2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
+        hi[j] = *reinterpret_cast<uint32_t*>(&hi2);
+        lo[j] = *reinterpret_cast<uint32_t*>(&lo2);
     }
     *reinterpret_cast<uint4*>(hi_dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(lo_dst) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -45,9 +47,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) dr_wgrad_tc_kernel(WgArgs g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * 128;
-    const float* A = g.A + (size_t)blockIdx.y * g.bsA;
-    const float* B = g.B + (size_t)blockIdx.y * g.bsB;
-    float* C = g.C + (size_t)blockIdx.y * g.bsC;
+    const float* __restrict__ A = (blockIdx.z ? g.A[1] : g.A[0]) + (size_t)blockIdx.y * g.bsA;
+    const float* __restrict__ B = (blockIdx.z ? g.B[1] : g.B[0]) + (size_t)blockIdx.y * g.bsB;
+    float* C = (blockIdx.z ? g.C[1] : g.C[0]) + (size_t)blockIdx.y * g.bsC;
     const uint32_t bpart = (uint32_t)g.Npad * 128u;                   // B tile part: Npad rows (n) x 64 k fp16
     const uint32_t stage_bytes = 2 * kWgAPart + 2 * bpart;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
@@ -77,27 +79,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) dr_wgrad_tc_kernel(WgArgs g) {
             uint8_t* sA = smem + (size_t)st * stage_bytes;
             uint8_t* sB = sA + 2 * kWgAPart;
             const int k0 = c * 64;
-            // all loads of a batch are issued before the first conversion (32 independent loads in flight per thread:
-            // the kernel streams ~1 KB per reduced row and is bound by memory-level parallelism otherwise)
-            {
-                float va[4][8];
+            // every load of the chunk's A tile and of the first B batch is issued before the first conversion (64 independent
+            // loads in flight per thread: the kernel streams ~1 KB per reduced row and is otherwise bound by memory latency)
+            for (int base = 0; base < g.Npad * 8; base += 4 * kWgConv) {
+                float va[4][8], vb[4][8];
+                if (base == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int kg = akg0 + 2 * i;
+                    for (int i = 0; i < 4; ++i) {
+                        const int kg = akg0 + 2 * i;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = k0 + kg * 8 + j;
-                        va[i][j] = (a_live && k < g.K) ? A[(size_t)k * g.lda + m0 + am] : 0.0f;
+                        for (int j = 0; j < 8; ++j) {
+                            const int k = k0 + kg * 8 + j;
+                            va[i][j] = (a_live && k < g.K) ? A[(size_t)k * g.lda + m0 + am] : 0.0f;
+                        }
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t o = sw128_offset(am, (akg0 + 2 * i) * 8);
-                    split8_store(va[i], g.a_scale, sA + o, sA + kWgAPart + o);
-                }
-            }
-            for (int base = 0; base < g.Npad * 8; base += 4 * kWgConv) {
-                float vb[4][8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int task = base + i * kWgConv + tid;
@@ -106,6 +102,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) dr_wgrad_tc_kernel(WgArgs g) {
                     for (int j = 0; j < 8; ++j) {
                         const int k = k0 + kg * 8 + j;
                         vb[i][j] = (task < g.Npad * 8 && n < g.N && k < g.K) ? B[(size_t)k * g.ldb + n] : 0.0f;
+                    }
+                }
+                if (base == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t o = sw128_offset(am, (akg0 + 2 * i) * 8);
+                        split8_store(va[i], g.a_scale, sA + o, sA + kWgAPart + o);
                     }
                 }
 #pragma unroll
@@ -181,19 +184,21 @@ int dr_grad_scale_log2(float inv_n) {
     return 3 - ex;
 }
 
-int dr_launch_wgrad_tc(dr_model* m, const float* A, long long lda, long long bsA, const float* B, long long ldb, long long bsB,
-                       float* C, long long ldc, long long bsC, int M, int N, int K, int batch, int a_scale_log2, int b_scale_log2,
-                       int accumulate) {
-    if (batch <= 0 || !dr_wgrad_tc_ok(M, N, K)) return DR_OK;
+// ndir problems (1 or 2: the GRU directions) with identical shapes and strides run in one grid (blockIdx.z)
+int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long lda, long long bsA, const float* const* B, long long ldb,
+                       long long bsB, float* const* C, long long ldc, long long bsC, int M, int N, int K, int batch, int a_scale_log2,
+                       int b_scale_log2, int accumulate) {
+    if (batch <= 0 || ndir < 1 || ndir > 2 || !dr_wgrad_tc_ok(M, N, K)) return DR_OK;
     WgArgs g;
-    g.A = A; g.lda = lda; g.bsA = bsA; g.B = B; g.ldb = ldb; g.bsB = bsB; g.C = C; g.ldc = ldc; g.bsC = bsC;
+    for (int d = 0; d < 2; ++d) { g.A[d] = A[d < ndir ? d : 0]; g.B[d] = B[d < ndir ? d : 0]; g.C[d] = C[d < ndir ? d : 0]; }
+    g.lda = lda; g.bsA = bsA; g.ldb = ldb; g.bsB = bsB; g.ldc = ldc; g.bsC = bsC;
     g.M = M; g.N = N; g.Npad = (N + 15) / 16 * 16; g.K = K;
     g.a_scale = ldexpf(1.0f, a_scale_log2); g.b_scale = ldexpf(1.0f, b_scale_log2);
     g.c_unscale = ldexpf(1.0f, -(a_scale_log2 + b_scale_log2));
     g.accumulate = accumulate;
     const size_t smem = 2 * (size_t)(2 * kWgAPart + 2 * g.Npad * 128) + 128;
     DR_CUDA(m, cudaFuncSetAttribute(dr_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * (2 * kWgAPart + 2 * 256 * 128) + 128)));
-    dim3 grid((M + 127) / 128, batch);
+    dim3 grid((M + 127) / 128, batch, ndir);
     dr_wgrad_tc_kernel<<<grid, kWgThreads, smem, m->stream>>>(g);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
