@@ -2,12 +2,18 @@
 // outputs, qrnn.py:43), pinball loss (qrnn.py:58-67), the backward that torch autograd derives
 // from qrnn.py:28-67 (adjoints listed in SURVEY §8a "Backward"), and Adam (estimate.py:61).
 //
-// Round-1 implementation: exact fp32 on the CUDA cores, organised as batched GEMMs + fused
-// elementwise kernels in TIME-MAJOR activations (row = t*Bm + b), one launch per time step and
-// direction for the recurrence.  It is the parity-complete training path (gradients of every
-// parameter family match the reference's autograd); moving its GEMMs to tcgen05 is later work.
-// Memory: 4.5 KB per expert-window-step-direction, so large batches are processed in micro-batches
-// of Bm windows (exact: windows are independent given the cross-expert sums, and gradients add).
+// Two engines behind the same state machine and the same activation layout (TIME-MAJOR rows, row = (e*T + t)*Bm + b):
+//  * tensor-core engine (default, cfg.engine != FFMA): the forward recurrence is the inference kernel instantiated to
+//    save (r,z,n), q, h per step (dr_gru_tc.cu, F <= 64); the reverse-time chain (gate adjoints + dh_{t-1} = dh*z +
+//    dgh W_hh) is one persistent tcgen05 kernel (dr_gru_bwd_tc.cu); the two weight-gradient reductions over all (t,b)
+//    rows are tcgen05 GEMMs whose fp32 sources are converted to split-fp16 operand images in flight (dr_wgrad_tc.cu).
+//    Split-fp16 (hi+lo, 3 tensor passes, fp32 accumulate) keeps every gradient tensor within the fp32 parity bounds of
+//    tests/test_gpu_train.py; gradient operands are scaled by an exact power of two chosen from 1/(M*B*T).
+//  * FFMA engine (cfg.engine == FFMA): exact fp32 on the CUDA cores — batched GEMMs (dr_bgemm_kernel) + elementwise
+//    kernels, one launch per time step and direction for both recurrences.  Cross-check of the other engine.
+// Dropout, the cross-expert sum, heads, loss, head/bias/mask gradients and Adam are fp32 elementwise kernels in both.
+// Memory: 4.5 KB per expert-window-step-direction, so large batches are processed in micro-batches of Bm windows sized
+// from the free HBM (exact: windows are independent given the cross-expert sums, and gradients add).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
