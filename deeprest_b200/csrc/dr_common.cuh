@@ -131,16 +131,17 @@ bool dr_tc_supported(const dr_model* m, int B, int T);
 int dr_tc_prep_weights(dr_model* m);
 int dr_launch_gru_tc(dr_model* m, const float* x_dev, int B, int T, float* S_dev, float* out_local_dev);
 // training forward of one micro-batch on the tensor-core engine: saves (r,z,n), q, h per step in dr_train.cu's layout
-int dr_launch_gru_tc_train(dr_model* m, const float* x_dev, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows);
+int dr_launch_gru_tc_train(dr_model* m, const float* x_dev, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows,
+                           int lane_major);
 // weight-gradient reductions C[z][m][n] (+)= sum_k A[z][k][m] B[z][k][n] on the tensor-core engine (dr_wgrad_tc.cu)
 bool dr_wgrad_tc_ok(int M, int N, int K);
 int dr_grad_scale_log2(float inv_n);
-int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long lda, long long bsA, const float* const* B, long long ldb,
-                       long long bsB, float* const* C, long long ldc, long long bsC, int M, int N, int K, int batch, int a_scale_log2,
-                       int b_scale_log2, int accumulate);
+int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long lda, long long bsA, const int* acol3 /* nullable */,
+                       const float* const* B, long long ldb, long long bsB, float* const* C, long long ldc, long long bsC,
+                       int M, int N, int K, int batch, int a_scale_log2, int b_scale_log2, int accumulate);
 // backward recurrence of one micro-batch on the tensor-core engine (dr_gru_bwd_tc.cu): gate adjoints + dh chain, in place
-int dr_launch_gru_bwd_tc(dr_model* m, float* rzn, float* gi, const float* q, const float* hs, const float* dhout,
-                         long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n);
+int dr_launch_gru_bwd_tc(dr_model* m, const float* rzn, const float* q, const float* hs, const float* dhout, float* g4,
+                         long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n, int in_lane_major);
 // dr_train.cu
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);

@@ -9,8 +9,8 @@
 //   TMEM          : D[128 x 128] fp32 (columns 0..127), the A operand dgh·2^ka as fp16 hi (columns 128..319) and
 //                   lo (columns 320..511) — written by the epilogue warps with tcgen05.st, consumed as MMA.TS.
 //   per step      : epilogue warps (thread = window row, warp/4 = hidden half) read r,z,n,q,h_prev,dh_out of step t,
-//                   form the gate adjoints (same formulas as dr_gate_bwd_kernel), store dgi / dgh for the weight-gradient
-//                   GEMMs in place, publish dgh to TMEM; the MMA thread issues 3 x 24 MMAs (hi·hi + hi·lo + lo·hi);
+//                   form the gate adjoints (same formulas as dr_gate_bwd_kernel), store (da_r, da_z, da_n, dq) for the
+//                   weight-gradient GEMMs, publish dgh to TMEM; the MMA thread issues 3 x 24 MMAs (hi·hi + hi·lo + lo·hi);
 //                   the epilogue adds D·2^-(ka+3) to the carried dh⊙z.  Strictly serial per step (a true dependency).
 // Gradients are O(1/(M·B·T)) — far below the fp16 range — so dgh is scaled by a power of two 2^ka chosen by the host
 // from 1/(M·B·T) (exact; undone on D), W_hh by 2^3 so that its lo parts stay out of the fp16 subnormals.
@@ -33,14 +33,19 @@ enum BwBar { BW_W_LAND = 0, BW_A_READY, BW_D_FULL, BW_NUM };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 
+// Input arrays are addressed as  block(dir, e, t) + (c/4)*sc + b*sb  (floats; c = column, b = window):
+//   row-major   [row][ncols] : sc = 4,    sb = ncols        (what the FFMA forward produces)
+//   lane-major  [c/4][b][4]  : sc = 4*B,  sb = 4            (what the tcgen05 forward and dr_dhout_kernel produce: a warp's
+//                                                            32 windows read one contiguous 512-byte run)
 struct BwdArgs {
     const uint8_t* wimg;      // [M_loc][2][kBwImg]
-    float* rzn;               // in: (r,z,n)  out: dgh = (da_r, da_z, dq)        [dir][ (e*T+t)*B + b ][3H]
-    float* gi;                // out: dgi = (da_r, da_z, da_n)                   same layout
-    const float* q;           // W_hn h + b_hn                                   [dir][row][H]
-    const float* hs;          // h_t                                             [dir][row][H]
-    const float* dhout;       // adjoint arriving from the heads                 [dir][ (e*T+t)*B + b ][H], dir stride dho_dir_rows
-    long long dir_rows;       // rows between the directions of rzn/gi/q/hs
+    const float* rzn;         // (r,z,n)                       block = (dir*dir_rows + (e*T+t)*B) * 3H
+    const float* q;           // W_hn h + b_hn                 block = (dir*dir_rows + (e*T+t)*B) * H
+    const float* dhout;       // adjoint arriving from the heads   block = (dir*dho_dir_rows + (e*T+t)*B) * H
+    const float* hs;          // h_t, row-major [dir][row][H]
+    float* g4;                // out, row-major [dir][row][4H] = (da_r, da_z, da_n, dq): dgi = columns 0..3H-1, dgh = 0..2H-1 | 3H..4H-1
+    long long rz_sc, rz_sb, q_sc, q_sb, do_sc, do_sb;
+    long long dir_rows;       // rows between the directions of rzn/q/hs/g4
     long long dho_dir_rows;   // rows between the directions of dhout
     int B, T, M_loc, ntiles;
     float a_scale;            // 2^ka
@@ -89,22 +94,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) dr_gru_bwd_tc_kernel(BwdArgs a
         for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
             const int t = dir ? (T - 1 - s) : s;
             const int tp = dir ? t + 1 : t - 1;                 // the step whose output was this step's h_prev
-            const size_t R = (size_t)dir * (size_t)a.dir_rows + ((size_t)e * T + t) * (size_t)B + bb;
+            const size_t blk = (size_t)dir * (size_t)a.dir_rows + ((size_t)e * T + t) * (size_t)B;       // first row of (dir, e, t)
+            const size_t R = blk + bb;
             const size_t Rp = (size_t)dir * (size_t)a.dir_rows + ((size_t)e * T + (s > 0 ? tp : t)) * (size_t)B + bb;
-            const size_t Rd = (size_t)dir * (size_t)a.dho_dir_rows + ((size_t)e * T + t) * (size_t)B + bb;
-            float* prz = a.rzn + R * (3 * DR_H) + half * 64;
-            float* pgi = a.gi + R * (3 * DR_H) + half * 64;
-            const float* pq = a.q + R * DR_H + half * 64;
+            const size_t dblk = (size_t)dir * (size_t)a.dho_dir_rows + ((size_t)e * T + t) * (size_t)B;
+            const float* prz = a.rzn + blk * (3 * DR_H) + bb * a.rz_sb;          // + (c/4)*rz_sc
+            const float* pq = a.q + blk * DR_H + bb * a.q_sb;                    // + (c/4)*q_sc
+            const float* pdo = a.dhout + dblk * DR_H + bb * a.do_sb;             // + (c/4)*do_sc
             const float* php = a.hs + Rp * DR_H + half * 64;
-            const float* pdo = a.dhout + Rd * DR_H + half * 64;
-            if (live && s > 0) {                                // next iteration's rows (step tp): warm L2 while this step runs
-                const long long step = (long long)(dir ? 1 : -1) * (long long)B;
-                const float* n_rz = prz + step * (3 * DR_H);
+            float* pg = a.g4 + R * (4 * DR_H) + half * 64;
+            const int c40 = half * 16;                                            // first column group (of 4) of this thread's half
+            if (live && s > 0) {                                // next iteration's blocks (step tp): warm L2 while this step runs
+                const long long nb = (long long)(dir ? 1 : -1) * (long long)B;  // rows to the next block
 #pragma unroll
-                for (int g = 0; g < 3; ++g) { prefetch_l2(n_rz + g * DR_H); prefetch_l2(n_rz + g * DR_H + 32); }
-                prefetch_l2(pq + step * DR_H); prefetch_l2(pq + step * DR_H + 32);
-                prefetch_l2(pdo + step * DR_H); prefetch_l2(pdo + step * DR_H + 32);
-                if (s > 1) { prefetch_l2(php + step * DR_H); prefetch_l2(php + step * DR_H + 32); }
+                for (int c4 = 0; c4 < 16; c4 += 8) {
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) prefetch_l2(prz + nb * (3 * DR_H) + (long long)(g * 32 + c40 + c4) * a.rz_sc);
+                    prefetch_l2(pq + nb * DR_H + (long long)(c40 + c4) * a.q_sc);
+                    prefetch_l2(pdo + nb * DR_H + (long long)(c40 + c4) * a.do_sc);
+                }
+                if (s > 1) { prefetch_l2(php + nb * DR_H); prefetch_l2(php + nb * DR_H + 32); }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                       // 16 hidden units at a time
@@ -112,11 +121,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) dr_gru_bwd_tc_kernel(BwdArgs a
                 if (live) {
 #pragma unroll
                     for (int v = 0; v < 16; v += 4) {
-                        const float4 x0 = *reinterpret_cast<const float4*>(prz + c * 16 + v);
-                        const float4 x1 = *reinterpret_cast<const float4*>(prz + DR_H + c * 16 + v);
-                        const float4 x2 = *reinterpret_cast<const float4*>(prz + 2 * DR_H + c * 16 + v);
-                        const float4 x3 = __ldg(reinterpret_cast<const float4*>(pq + c * 16 + v));
-                        const float4 x5 = __ldg(reinterpret_cast<const float4*>(pdo + c * 16 + v));
+                        const long long c4 = c40 + c * 4 + (v >> 2);            // column group inside one gate / inside q, dhout
+                        const float4 x0 = __ldg(reinterpret_cast<const float4*>(prz + c4 * a.rz_sc));
+                        const float4 x1 = __ldg(reinterpret_cast<const float4*>(prz + (c4 + 32) * a.rz_sc));
+                        const float4 x2 = __ldg(reinterpret_cast<const float4*>(prz + (c4 + 64) * a.rz_sc));
+                        const float4 x3 = __ldg(reinterpret_cast<const float4*>(pq + c4 * a.q_sc));
+                        const float4 x5 = __ldg(reinterpret_cast<const float4*>(pdo + c4 * a.do_sc));
                         float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (s > 0) x4 = __ldg(reinterpret_cast<const float4*>(php + c * 16 + v));
                         r_[v] = x0.x; r_[v + 1] = x0.y; r_[v + 2] = x0.z; r_[v + 3] = x0.w;
@@ -146,14 +156,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) dr_gru_bwd_tc_kernel(BwdArgs a
                 if (live) {
 #pragma unroll
                     for (int v = 0; v < 16; v += 4) {
-                        const float4 o0 = make_float4(dar[v], dar[v + 1], dar[v + 2], dar[v + 3]);
-                        const float4 o1 = make_float4(daz[v], daz[v + 1], daz[v + 2], daz[v + 3]);
-                        *reinterpret_cast<float4*>(pgi + c * 16 + v) = o0;
-                        *reinterpret_cast<float4*>(pgi + DR_H + c * 16 + v) = o1;
-                        *reinterpret_cast<float4*>(pgi + 2 * DR_H + c * 16 + v) = make_float4(dan[v], dan[v + 1], dan[v + 2], dan[v + 3]);
-                        *reinterpret_cast<float4*>(prz + c * 16 + v) = o0;
-                        *reinterpret_cast<float4*>(prz + DR_H + c * 16 + v) = o1;
-                        *reinterpret_cast<float4*>(prz + 2 * DR_H + c * 16 + v) = make_float4(dq[v], dq[v + 1], dq[v + 2], dq[v + 3]);
+                        *reinterpret_cast<float4*>(pg + c * 16 + v) = make_float4(dar[v], dar[v + 1], dar[v + 2], dar[v + 3]);
+                        *reinterpret_cast<float4*>(pg + DR_H + c * 16 + v) = make_float4(daz[v], daz[v + 1], daz[v + 2], daz[v + 3]);
+                        *reinterpret_cast<float4*>(pg + 2 * DR_H + c * 16 + v) = make_float4(dan[v], dan[v + 1], dan[v + 2], dan[v + 3]);
+                        *reinterpret_cast<float4*>(pg + 3 * DR_H + c * 16 + v) = make_float4(dq[v], dq[v + 1], dq[v + 2], dq[v + 3]);
                     }
                 }
                 if (s > 0) {                                    // A operand of this step's product: split-fp16 dgh·2^ka into TMEM
@@ -260,9 +266,10 @@ __global__ void dr_tc_pack_whT_kernel(const float* __restrict__ blob, DrBlobOffs
 
 }  // namespace
 
-// Backward recurrence of one micro-batch, both directions, all local experts.  rzn/gi/q/hs/dhout in dr_train.cu's layouts.
-int dr_launch_gru_bwd_tc(dr_model* m, float* rzn, float* gi, const float* q, const float* hs, const float* dhout,
-                         long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n) {
+// Backward recurrence of one micro-batch, both directions, all local experts.  in_lane_major: layout of rzn and q (see BwdArgs);
+// dhout is always lane-major here (dr_dhout_kernel writes it that way for this engine); g4 is [dir][row][4H] row-major.
+int dr_launch_gru_bwd_tc(dr_model* m, const float* rzn, const float* q, const float* hs, const float* dhout, float* g4,
+                         long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n, int in_lane_major) {
     const int Ml = m->M_loc;
     if (Ml == 0 || Bm <= 0 || T <= 0) return DR_OK;
     const size_t bytes = (size_t)Ml * 2 * kBwImg;
@@ -278,7 +285,10 @@ int dr_launch_gru_bwd_tc(dr_model* m, float* rzn, float* gi, const float* q, con
     const int ka = dr_grad_scale_log2(inv_n);
     BwdArgs a;
     a.wimg = reinterpret_cast<const uint8_t*>(m->d_whT);
-    a.rzn = rzn; a.gi = gi; a.q = q; a.hs = hs; a.dhout = dhout;
+    a.rzn = rzn; a.q = q; a.hs = hs; a.dhout = dhout; a.g4 = g4;
+    a.rz_sc = in_lane_major ? 4LL * Bm : 4; a.rz_sb = in_lane_major ? 4 : 3 * DR_H;
+    a.q_sc = in_lane_major ? 4LL * Bm : 4;  a.q_sb = in_lane_major ? 4 : DR_H;
+    a.do_sc = 4LL * Bm; a.do_sb = 4;
     a.dir_rows = dir_rows; a.dho_dir_rows = dho_dir_rows;
     a.B = Bm; a.T = T; a.M_loc = Ml; a.ntiles = (Bm + 127) / 128;
     a.a_scale = ldexpf(1.0f, ka);

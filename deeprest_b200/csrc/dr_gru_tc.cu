@@ -74,7 +74,10 @@ __device__ __forceinline__ void store_bhn(uint32_t taddr, const float* src) {
 // backward pass of csrc/dr_train.cu consumes, in its layout: row = (e*T + t)*B + b (B = the micro-batch of this launch),
 //   rzn[dir][row][3H] = (r, z, n)    q[dir][row][H] = W_hn h_{t-1} + b_hn    hs[dir][row][H] = h_t
 // with dir_stride_rows rows between the two directions.  Dropout, S and the heads are applied by the training kernels.
-struct TcTrainOut { float* rzn; float* q; float* hs; long long dir_stride_rows; };
+// lane_major != 0: rzn and q are written window-contiguous inside each (dir, e, t) block — element (column c, window b) at
+//   block + ((c/4)*B + b)*4 + c%4 — so that this kernel's stores (thread = window) and the backward kernel's loads are
+//   coalesced 512-byte runs per warp instead of 16 bytes per lane per row.  hs stays row-major (read by the head kernels).
+struct TcTrainOut { float* rzn; float* q; float* hs; long long dir_stride_rows; int lane_major; };
 
 template <bool kTiming, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
@@ -327,16 +330,20 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         plo[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
                     }
                     if (kTrain && live) {
-                        float* pr = tr.rzn + trow * (3 * DR_H) + u0 + j8;
-                        float* pq = tr.q + trow * DR_H + u0 + j8;
                         float* ph = tr.hs + trow * DR_H + u0 + j8;
+                        // (column c, this window): row-major  trow*ncols + c   |   lane-major  block + ((c/4)*B + b)*4
+                        const size_t blk = trow - (size_t)b;                     // first row of the (dir, e, t) block
+                        const size_t cs = tr.lane_major ? (size_t)B : 1;        // float4 slots between consecutive column groups
+                        float* pr = tr.lane_major ? tr.rzn + blk * (3 * DR_H) + (size_t)b * 4 : tr.rzn + trow * (3 * DR_H);
+                        float* pq = tr.lane_major ? tr.q + blk * DR_H + (size_t)b * 4 : tr.q + trow * DR_H;
 #pragma unroll
                         for (int v = 0; v < 8; v += 4) {
-                            *reinterpret_cast<float4*>(pr + v) = make_float4(rv[v], rv[v + 1], rv[v + 2], rv[v + 3]);
-                            *reinterpret_cast<float4*>(pr + DR_H + v) = make_float4(zz[v], zz[v + 1], zz[v + 2], zz[v + 3]);
-                            *reinterpret_cast<float4*>(pr + 2 * DR_H + v) = make_float4(nv[v], nv[v + 1], nv[v + 2], nv[v + 3]);
-                            *reinterpret_cast<float4*>(pq + v) = make_float4(__uint_as_float(gh[j8 + v]), __uint_as_float(gh[j8 + v + 1]),
-                                                                             __uint_as_float(gh[j8 + v + 2]), __uint_as_float(gh[j8 + v + 3]));
+                            const size_t c4 = (size_t)((u0 + j8 + v) >> 2);
+                            *reinterpret_cast<float4*>(pr + c4 * cs * 4) = make_float4(rv[v], rv[v + 1], rv[v + 2], rv[v + 3]);
+                            *reinterpret_cast<float4*>(pr + (c4 + DR_H / 4) * cs * 4) = make_float4(zz[v], zz[v + 1], zz[v + 2], zz[v + 3]);
+                            *reinterpret_cast<float4*>(pr + (c4 + 2 * DR_H / 4) * cs * 4) = make_float4(nv[v], nv[v + 1], nv[v + 2], nv[v + 3]);
+                            *reinterpret_cast<float4*>(pq + c4 * cs * 4) = make_float4(__uint_as_float(gh[j8 + v]), __uint_as_float(gh[j8 + v + 1]),
+                                                                                       __uint_as_float(gh[j8 + v + 2]), __uint_as_float(gh[j8 + v + 3]));
                             *reinterpret_cast<float4*>(ph + v) = make_float4(hn[j8 + v], hn[j8 + v + 1], hn[j8 + v + 2], hn[j8 + v + 3]);
                         }
                     }
@@ -610,7 +617,8 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
 // Training forward of one micro-batch on the tensor-core engine: the same recurrence kernel, instantiated to save the
 // per-step activations (r, z, n, q, h) the backward pass needs instead of producing S and head partials (the training
 // kernels apply dropout, the cross-expert sum and the heads from hs).  x points at the first window of the micro-batch.
-int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows) {
+int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rzn, float* q, float* hs, long long dir_stride_rows,
+                           int lane_major) {
     if (m->M_loc == 0 || Bm <= 0 || T <= 0) return DR_OK;
     const int ntiles = (Bm + 255) / 256, Bp = (Bm + 127) / 128 * 128;
     const size_t xbytes = (size_t)T * ntiles * 2 * kXStage;
@@ -626,7 +634,7 @@ int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rz
     const int items = m->M_loc * 2 * ntiles;
     dr_gru_tc_kernel<false, true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
         reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc_tr), m->d_bias4, m->d_ct,
-        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows});
+        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows, lane_major});
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
     return DR_OK;

@@ -265,11 +265,14 @@ __global__ void dr_gbar_kernel(const float* __restrict__ dy, const float* __rest
 // d(h_t) that enters the GRU backward: dropout adjoint of (Ct^T dy + Gbar)     dhout[d][e][(t,b)][H]
 __global__ void dr_dhout_kernel(const float* __restrict__ dy, const float* __restrict__ gbar, const float* __restrict__ ct,
                                 const uint8_t* __restrict__ mask, uint64_t seed, float p, float* __restrict__ dhout,
-                                int M_loc, int e_lo, int B, int b0, int Bm, int T, size_t total) {
+                                int M_loc, int e_lo, int B, int b0, int Bm, int T, size_t total, int lane_major) {
     size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;           // one thread = 4 consecutive hidden units
     if (i4 * 4 >= total) return;
-    int j = (int)(i4 % (DR_H / 4)) * 4; size_t r = i4 / (DR_H / 4);
-    int b = (int)(r % Bm); r /= Bm;
+    // row-major output [d][e][t][b][H] (i4 walks it in order), or lane-major [d][e][t][H/4][b][4] for the tensor-core
+    // backward kernel (windows fastest: the stores stay coalesced, the strided gbar reads come from L2)
+    int j, b; size_t r;
+    if (lane_major) { b = (int)(i4 % Bm); r = i4 / Bm; j = (int)(r % (DR_H / 4)) * 4; r /= DR_H / 4; }
+    else            { j = (int)(i4 % (DR_H / 4)) * 4; r = i4 / (DR_H / 4); b = (int)(r % Bm); r /= Bm; }
     int t = (int)(r % T); r /= T;
     int e = (int)(r % M_loc); int d = (int)(r / M_loc);
     int k = d * DR_H + j;
@@ -353,6 +356,20 @@ __global__ void dr_colsum_kernel(const float* __restrict__ src, float* __restric
     float acc = 0.0f;
     for (size_t r = r0; r < r1; ++r) acc += src[((size_t)e * rows + r) * 3 * DR_H + c];
     atomicAdd(gblob + (size_t)e * pe + off + c, acc);
+}
+
+// tensor-core path: g4[e][row][4H] = (da_r, da_z, da_n, dq);  db_ih += sums of columns 0..3H-1,  db_hh += (da_r, da_z, dq)
+__global__ void dr_colsum4_kernel(const float* __restrict__ g4, float* __restrict__ gblob, int off_bih, int off_bhh, int pe,
+                                  size_t rows, int rows_per_chunk) {
+    int e = blockIdx.x, c = threadIdx.x;                                  // 4H threads
+    size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+    if (r1 > rows) r1 = rows;
+    float acc = 0.0f;
+    for (size_t r = r0; r < r1; ++r) acc += g4[((size_t)e * rows + r) * 4 * DR_H + c];
+    float* gb = gblob + (size_t)e * pe;
+    if (c < 3 * DR_H) atomicAdd(gb + off_bih + c, acc);
+    if (c < 2 * DR_H) atomicAdd(gb + off_bhh + c, acc);
+    else if (c >= 3 * DR_H) atomicAdd(gb + off_bhh + c - DR_H, acc);
 }
 
 // from P[e][3H][F] = sum dgi (x) x :  dW_ih += P * mask ;  dmask[e][f] += sum_i W_ih[i][f] P[i][f]
@@ -451,7 +468,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     const int F = m->cfg.F, Ml = m->M_loc, pe = m->off.per_expert;
     if (m->cfg.dropout_p >= 1.0f) return dr_fail(m, DR_EINVAL, "dropout_p must be < 1");
     // micro-batch size from a memory budget (4.5 KB per expert-window-step-direction, see header)
-    size_t per_window = (size_t)2 * Ml * T * (3 * DR_H * 2 + DR_H * 3) * sizeof(float);
+    size_t per_window = (size_t)2 * Ml * T * (3 * DR_H + 4 * DR_H + DR_H * 3) * sizeof(float);   // rzn, gi/g4, q+hs+dhout
     // budget: half of the HBM that is free right now plus what this workspace already holds, at least 8 GB (a 180 GB
     // B200 gives ~85 GB: config-2-sized micro-batches of 256+ windows stay in one piece, so nothing is recomputed and
     // the per-step GEMMs of the backward chain run on full 128-row tiles)
@@ -460,7 +477,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             const dr_train_ws* cur = reinterpret_cast<const dr_train_ws*>(m->train_ws);
-            size_t held = cur ? (size_t)2 * Ml * cur->cap_rows * (3 * DR_H * 2 + DR_H * 3) * sizeof(float) : 0;
+            size_t held = cur ? (size_t)2 * Ml * cur->cap_rows * (3 * DR_H + 4 * DR_H + DR_H * 3) * sizeof(float) : 0;
             budget = std::max<size_t>((size_t)8 << 30, (free_b + held) / 2);
         }
     }
@@ -472,7 +489,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     size_t rows = (size_t)T * Bm, E2 = (size_t)2 * Ml;
     if (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T) {
         int rc;
-        if ((rc = ws_alloc(m, &ws->xt, rows * F)) || (rc = ws_alloc(m, &ws->gi, E2 * rows * 3 * DR_H)) ||
+        if ((rc = ws_alloc(m, &ws->xt, rows * F)) || (rc = ws_alloc(m, &ws->gi, E2 * rows * 4 * DR_H)) ||
             (rc = ws_alloc(m, &ws->rzn, E2 * rows * 3 * DR_H)) || (rc = ws_alloc(m, &ws->q, E2 * rows * DR_H)) ||
             (rc = ws_alloc(m, &ws->hs, E2 * rows * DR_H)) || (rc = ws_alloc(m, &ws->dhout, E2 * rows * DR_H)) ||
             (rc = ws_alloc(m, &ws->gh, (size_t)Ml * Bm * 3 * DR_H)) || (rc = ws_alloc(m, &ws->dhc, (size_t)Ml * Bm * DR_H)) ||
@@ -509,9 +526,10 @@ static int train_forward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     dr_time_major_kernel<<<nblk(r * F), 256, 0, st>>>(ws->x, ws->xt, b0, bm, T, F);
     // Tensor-core engine: the whole recurrence of the micro-batch (both directions, all experts) is ONE launch of the
     // tcgen05 kernel of the inference path, instantiated to save (r,z,n), q and h per step (csrc/dr_gru_tc.cu).
-    const bool tc_fwd = m->cfg.engine != DR_ENGINE_FFMA && dr_tc_supported(m, bm, T) && m->d_wtc != nullptr;
+    const bool tc_fwd = m->cfg.engine != DR_ENGINE_FFMA && dr_tc_supported(m, bm, T) && m->d_wtc != nullptr;   // == train_tc_forward()
     if (tc_fwd) {
-        int rc = dr_launch_gru_tc_train(m, ws->x + (size_t)b0 * T * F, bm, T, ws->rzn, ws->q, ws->hs, (long long)ed_stride);
+        // rzn and q window-contiguous (lane-major): only the tensor-core backward kernel reads them
+        int rc = dr_launch_gru_tc_train(m, ws->x + (size_t)b0 * T * F, bm, T, ws->rzn, ws->q, ws->hs, (long long)ed_stride, 1);
         if (rc) return rc;
     }
     for (int d = 0; d < 2 && !tc_fwd; ++d) {
@@ -549,6 +567,11 @@ static int train_forward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     return DR_OK;
 }
 
+// the forward recurrence of this micro-batch runs (ran) on the tensor-core kernel: rzn and q are lane-major then
+static bool train_tc_forward(const dr_model* m, int bm, int T) {
+    return m->cfg.engine != DR_ENGINE_FFMA && dr_tc_supported(m, bm, T) && m->d_wtc != nullptr;
+}
+
 // backward of micro-batch mb (G-bar already complete in ws->gbar)
 static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     const int F = m->cfg.F, Ml = m->M_loc, M = m->cfg.M, pe = m->off.per_expert, T = ws->T, B = ws->B;
@@ -557,8 +580,10 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     const size_t r = (size_t)T * bm;
     const size_t ed_stride = (size_t)Ml * ws->cap_rows;
     size_t td = (size_t)2 * Ml * r * DR_H;
-    // dhout is laid out [d][e][(t,b)][H] with the (t,b) row stride of this micro-batch
-    if (td) dr_dhout_kernel<<<nblk(td / 4), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, ws->mask, ws->seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td);
+    const bool tc_bwd = m->cfg.engine != DR_ENGINE_FFMA && Ml > 0;
+    // dhout [d][e][t] blocks of bm windows x H: row-major for the FFMA chain, window-contiguous for the tensor-core kernel
+    if (td) dr_dhout_kernel<<<nblk(td / 4), 256, 0, st>>>(ws->dy, ws->gbar, m->d_ct, ws->mask, ws->seed, p, ws->dhout, Ml, m->e_lo, B, b0, bm, T, td,
+                                                           tc_bwd ? 1 : 0);
     if (Ml) {
         int chunk = 2048;
         dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
@@ -567,51 +592,69 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
     }
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
-    // Tensor-core engine: the reverse-time chain (gate adjoints + dh_{t-1} = dh*z + dgh W_hh) of both directions and all
-    // experts is ONE persistent tcgen05 kernel (csrc/dr_gru_bwd_tc.cu) instead of 2(T-1) x {gate kernel, fp32 GEMM}.
-    const bool tc_bwd = m->cfg.engine != DR_ENGINE_FFMA && Ml > 0;
-    const bool tc_wgrad = tc_bwd && getenv("DR_TRAIN_WGRAD_FFMA") == nullptr;      // escape hatch: keep the fp32 GEMMs
-    if (tc_bwd) {
-        int rc = dr_launch_gru_bwd_tc(m, ws->rzn, ws->gi, ws->q, ws->hs, ws->dhout, (long long)ed_stride, (long long)((size_t)Ml * r), bm, T,
-                                      1.0f / ((float)M * (float)B * (float)T));
-        if (rc) return rc;
-    }
-    // weight gradients over all (t,b) rows of the micro-batch; dW_hh skips the step whose h_prev is the zero initial state.
-    // Tensor-core engine: split-fp16 tcgen05 reductions (csrc/dr_wgrad_tc.cu), both directions in one grid, the gradient
-    // operand scaled by the same power of two as in the recurrence kernel and h / x by 2^4.
-    const size_t skip = (size_t)bm;
+    const size_t skip = (size_t)bm;                             // dW_hh skips the step whose h_prev is the zero initial state
     const size_t p_dir = (size_t)Ml * 3 * DR_H * F;             // ws->P holds one [Ml][3H][F] block per direction
-    const bool p_tc = tc_wgrad && dr_wgrad_tc_ok(3 * DR_H, F, (int)r);
-    if (tc_wgrad) {
-        const int ka = dr_grad_scale_log2(1.0f / ((float)M * (float)B * (float)T));
+
+    if (tc_bwd) {
+        // ---------------- tensor-core engine ----------------
+        // (1) the reverse-time chain (gate adjoints + dh_{t-1} = dh*z + dgh W_hh) of both directions and all experts is ONE
+        //     persistent tcgen05 kernel (csrc/dr_gru_bwd_tc.cu); it leaves g4 = (da_r, da_z, da_n, dq) per row in ws->gi
+        const float inv_n = 1.0f / ((float)M * (float)B * (float)T);
+        int rc = dr_launch_gru_bwd_tc(m, ws->rzn, ws->q, ws->hs, ws->dhout, ws->gi, (long long)ed_stride, (long long)((size_t)Ml * r), bm, T,
+                                      inv_n, train_tc_forward(m, bm, T) ? 1 : 0);
+        if (rc) return rc;
+        // (2) the reductions over all (t,b) rows as split-fp16 tcgen05 GEMMs (csrc/dr_wgrad_tc.cu), both directions per grid;
+        //     the gradient operand is scaled by the same power of two as in (1), h / x by 2^4.  A = columns of g4:
+        //     dW_hh uses (da_r, da_z, dq) = column blocks {0, H, 3H},  P = dgi^T x uses (da_r, da_z, da_n) = {0, H, 2H}
+        const int ka = dr_grad_scale_log2(inv_n);
+        const long long g4e = (long long)T * bm * 4 * DR_H;                             // floats per expert in g4
+        const bool p_tc = dr_wgrad_tc_ok(3 * DR_H, F, (int)r);
         const float *Aw[2], *Bw[2], *Ap[2], *Bx[2];
         float *Cw[2], *Cp[2];
         for (int d = 0; d < 2; ++d) {
-            Aw[d] = ws->rzn + d * ed_stride * 3 * DR_H + (d ? 0 : skip * 3 * DR_H);    // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
+            const float* g4d = ws->gi + d * ed_stride * 4 * DR_H;
+            Aw[d] = g4d + (d ? 0 : skip * 4 * DR_H);                                     // rows t>=1 (fwd) / t<=T-2 (rev)
             Bw[d] = ws->hs + d * ed_stride * DR_H + (d ? skip * DR_H : 0);              // h_{t-1} (fwd) / h_{t+1} (rev)
             Cw[d] = m->d_grad + m->off.w_hh[d];
-            Ap[d] = ws->gi + d * ed_stride * 3 * DR_H; Bx[d] = ws->xt; Cp[d] = ws->P + d * p_dir;
+            Ap[d] = g4d; Bx[d] = ws->xt; Cp[d] = ws->P + d * p_dir;
         }
+        const int cols_whh[3] = {0, DR_H, 3 * DR_H}, cols_p[3] = {0, DR_H, 2 * DR_H};
         if (T > 1) {
-            int rc = dr_launch_wgrad_tc(m, 2, Aw, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bw, DR_H, (long long)T * bm * DR_H, Cw, DR_H,
-                                        (long long)pe, 3 * DR_H, DR_H, (int)(r - skip), Ml, ka, 4, 1);
+            rc = dr_launch_wgrad_tc(m, 2, Aw, 4 * DR_H, g4e, cols_whh, Bw, DR_H, (long long)T * bm * DR_H, Cw, DR_H, (long long)pe,
+                                    3 * DR_H, DR_H, (int)(r - skip), Ml, ka, 4, 1);
             if (rc) return rc;
         }
         if (p_tc) {
-            int rc = dr_launch_wgrad_tc(m, 2, Ap, 3 * DR_H, (long long)T * bm * 3 * DR_H, Bx, F, 0, Cp, F, (long long)3 * DR_H * F,
-                                        3 * DR_H, F, (int)r, Ml, ka, 4, 0);
+            rc = dr_launch_wgrad_tc(m, 2, Ap, 4 * DR_H, g4e, cols_p, Bx, F, 0, Cp, F, (long long)3 * DR_H * F, 3 * DR_H, F, (int)r, Ml, ka, 4, 0);
             if (rc) return rc;
         }
+        for (int d = 0; d < 2; ++d) {
+            const float* g4d = ws->gi + d * ed_stride * 4 * DR_H;
+            float* Pd = ws->P + d * p_dir;
+            if (!p_tc) {                                        // F > 256: fp32 GEMM on the dgi columns of g4 (row stride 4H)
+                Gemm gp{g4d, ws->xt, Pd, 3 * DR_H, F, (int)r, 1, 4 * DR_H, F, 1, F, 1, (long)g4e, 0, (long)3 * DR_H * F, 0.0f};
+                rc = gemm(m, gp, Ml);
+                if (rc) return rc;
+            }
+            dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(Pd, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
+            int chunk = 1024;
+            dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
+            dr_colsum4_kernel<<<grid, 4 * DR_H, 0, st>>>(g4d, m->d_grad, m->off.b_ih[d], m->off.b_hh[d], pe, r, chunk);
+            DR_CUDA(m, cudaGetLastError());
+            m->launches += 2;
+        }
+        return DR_OK;
     }
+
+    // ---------------- FFMA engine: exact fp32, one gate kernel + one GEMM per time step and direction ----------------
     for (int d = 0; d < 2 && Ml; ++d) {
         float* gi = ws->gi + d * ed_stride * 3 * DR_H;
         float* rzn = ws->rzn + d * ed_stride * 3 * DR_H;
         float* q = ws->q + d * ed_stride * DR_H;
         float* hs = ws->hs + d * ed_stride * DR_H;
         float* dho = ws->dhout + (size_t)d * Ml * r * DR_H;
-        float* Pd = ws->P + (p_tc ? d * p_dir : 0);
-        if (!tc_bwd) DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
-        for (int s = T - 1; s >= 0 && !tc_bwd; --s) {           // reverse of the forward processing order
+        DR_CUDA(m, cudaMemsetAsync(ws->dhc, 0, (size_t)Ml * bm * DR_H * sizeof(float), st));
+        for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
             const int t = d ? (T - 1 - s) : s, tp = d ? t + 1 : t - 1;
             const float* hprev = (s == 0) ? nullptr : hs + (size_t)tp * bm * DR_H;
             size_t tg = (size_t)Ml * bm * DR_H;
@@ -623,27 +666,26 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
                 if (rc) return rc;
             }
         }
-        if (!tc_wgrad && T > 1) {
-            const float* A = rzn + (d ? 0 : skip * 3 * DR_H);
-            const float* Bp = hs + (d ? skip * DR_H : 0);
+        // weight gradients as GEMMs over all (t,b) rows of the micro-batch
+        if (T > 1) {
+            const float* A = rzn + (d ? 0 : skip * 3 * DR_H);     // dgh rows for t>=1 (fwd) / t<=T-2 (rev)
+            const float* Bp = hs + (d ? skip * DR_H : 0);         // h_{t-1} (fwd) / h_{t+1} (rev)
             Gemm gw{A, Bp, m->d_grad + m->off.w_hh[d], 3 * DR_H, DR_H, (int)(r - skip),
                     1, 3 * DR_H, DR_H, 1, DR_H, 1, (long)T * bm * 3 * DR_H, (long)T * bm * DR_H, (long)pe, 1.0f};
             int rc = gemm(m, gw, Ml);
             if (rc) return rc;
         }
-        if (!p_tc) {
-            Gemm gp{gi, ws->xt, Pd, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
-                    (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
-            int rc = gemm(m, gp, Ml);
-            if (rc) return rc;
-        }
-        dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(Pd, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
+        Gemm gp{gi, ws->xt, ws->P, 3 * DR_H, F, (int)r, 1, 3 * DR_H, F, 1, F, 1,
+                (long)T * bm * 3 * DR_H, 0, (long)3 * DR_H * F, 0.0f};
+        int rc = gemm(m, gp, Ml);
+        if (rc) return rc;
+        dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->P, m->d_blob, m->d_mask, m->d_grad, ws->dmask, m->off.w_ih[d], pe, F);
         int chunk = 1024;
         dim3 grid(Ml, (unsigned)((r + chunk - 1) / chunk));
         dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(rzn, m->d_grad, m->off.b_hh[d], pe, r, chunk);
         dr_colsum_kernel<<<grid, 3 * DR_H, 0, st>>>(gi, m->d_grad, m->off.b_ih[d], pe, r, chunk);
         DR_CUDA(m, cudaGetLastError());
-        m->launches += tc_bwd ? 5 : 3 + 2 * T;
+        m->launches += 3 + 2 * T;
     }
     return DR_OK;
 }

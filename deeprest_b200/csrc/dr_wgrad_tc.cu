@@ -23,6 +23,7 @@ struct WgArgs {                                       // blockIdx.z selects one 
     const float* B[2]; long long ldb, bsB;
     float* C[2]; long long ldc, bsC;
     int M, N, Npad, K;
+    int acol[3];              // A column of the first row of m-tile 0, 1, 2 (-1: m-tile i starts at column 128*i)
     float a_scale, b_scale, c_unscale;
     int accumulate;
 };
@@ -73,6 +74,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) dr_wgrad_tc_kernel(WgArgs g) {
         // ===================== converters: fp32 [k][m] / [k][n] -> split-fp16 K-major images =====================
         const int am = tid & 127, akg0 = tid >> 7;                      // A: row m, k-groups akg0, akg0+2, akg0+4, akg0+6
         const bool a_live = m0 + am < g.M;
+        // the m-tile's 128 source columns need not sit at column m0 of A (dW_hh takes (da_r, da_z, dq) out of 4H-wide rows)
+        const int amap = (blockIdx.x == 0) ? g.acol[0] : (blockIdx.x == 1) ? g.acol[1] : (blockIdx.x == 2) ? g.acol[2] : -1;
+        const int acol = (amap >= 0 ? amap : m0) + am;
         for (int c = 0; c < nchunks; ++c) {
             const int st = c & 1;
             if (c >= 2) mbar_wait(bar(WG_EMPTY0 + st), (uint32_t)(((c >> 1) - 1) & 1));   // MMAs of chunk c-2 have read this stage
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) dr_wgrad_tc_kernel(WgArgs g) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int k = k0 + kg * 8 + j;
-                            va[i][j] = (a_live && k < g.K) ? A[(size_t)k * g.lda + m0 + am] : 0.0f;
+                            va[i][j] = (a_live && k < g.K) ? A[(size_t)k * g.lda + acol] : 0.0f;
                         }
                     }
                 }
@@ -185,14 +189,15 @@ int dr_grad_scale_log2(float inv_n) {
 }
 
 // ndir problems (1 or 2: the GRU directions) with identical shapes and strides run in one grid (blockIdx.z)
-int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long lda, long long bsA, const float* const* B, long long ldb,
-                       long long bsB, float* const* C, long long ldc, long long bsC, int M, int N, int K, int batch, int a_scale_log2,
-                       int b_scale_log2, int accumulate) {
+int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long lda, long long bsA, const int* acol3 /* nullable */,
+                       const float* const* B, long long ldb, long long bsB, float* const* C, long long ldc, long long bsC,
+                       int M, int N, int K, int batch, int a_scale_log2, int b_scale_log2, int accumulate) {
     if (batch <= 0 || ndir < 1 || ndir > 2 || !dr_wgrad_tc_ok(M, N, K)) return DR_OK;
     WgArgs g;
     for (int d = 0; d < 2; ++d) { g.A[d] = A[d < ndir ? d : 0]; g.B[d] = B[d < ndir ? d : 0]; g.C[d] = C[d < ndir ? d : 0]; }
     g.lda = lda; g.bsA = bsA; g.ldb = ldb; g.bsB = bsB; g.ldc = ldc; g.bsC = bsC;
     g.M = M; g.N = N; g.Npad = (N + 15) / 16 * 16; g.K = K;
+    for (int i = 0; i < 3; ++i) g.acol[i] = acol3 ? acol3[i] : -1;
     g.a_scale = ldexpf(1.0f, a_scale_log2); g.b_scale = ldexpf(1.0f, b_scale_log2);
     g.c_unscale = ldexpf(1.0f, -(a_scale_log2 + b_scale_log2));
     g.accumulate = accumulate;
