@@ -43,9 +43,9 @@ extern "C" {
 #define DR_Q 3
 
 /* engine selection for the bi-GRU recurrence */
-#define DR_ENGINE_AUTO  0    /* tcgen05 for large batches, FFMA for small ones              */
+#define DR_ENGINE_AUTO  0    /* tcgen05 where it applies (F <= 64 for the forward), else FFMA */
 #define DR_ENGINE_FFMA  1    /* fp32 CUDA-core kernel (exact fp32 accumulate)               */
-#define DR_ENGINE_TC    2    /* tcgen05 tensor-core kernel, split-bf16 (3-pass) operands    */
+#define DR_ENGINE_TC    2    /* tcgen05 tensor-core kernels, split-fp16 (3-pass) operands   */
 
 typedef struct dr_model dr_model;
 
@@ -146,7 +146,9 @@ int  dr_quantile_loss_dev(dr_model* m, const float* out_dev, const float* y_dev,
  * with torch.optim.Adam(lr) defaults (estimate.py:61); Adam state lives in the handle.
  * x [B,T,F], y [B,T,M].  dropout_mask (nullable): replayed keep-mask, uint8 [M,B,T,2H] in the
  * reference's rnn_out element order (parity tests); NULL -> counter-based RNG keyed by `seed`.
- * Round 1: world must be 1.  dr_get_grads returns the gradients of the last step (blob order). */
+ * dr_train_step(_dev) need world == 1 (sharded handles: dr_train_begin_dev / dr_train_advance below).  With engine AUTO / TC
+ * the two recurrences and the weight-gradient reductions run on tcgen05 (split-fp16, fp32 accumulate), with engine FFMA the
+ * whole step is exact fp32 on the CUDA cores.  dr_get_grads returns the gradients of the last step (blob order). */
 int  dr_train_step    (dr_model* m, const float* x_host, const float* y_host, int32_t B, int32_t T,
                        const uint8_t* dropout_mask_host, uint64_t seed, float lr, float* loss_host);
 int  dr_train_step_dev(dr_model* m, const float* x_dev, const float* y_dev, int32_t B, int32_t T,
