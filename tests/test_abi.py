@@ -101,3 +101,12 @@ def test_series_window_count_matches_reference_sliding_window():
     for N, W, stride in [(150, 20, 1), (150, 20, 7), (150, 20, 20), (20, 20, 1), (21, 20, 1), (3, 60, 1), (100, 60, 60)]:
         ref = len(oracle.sliding_window(np.zeros((N, 2)), W)[::stride]) if N - W > 0 else 0
         assert lib.dr_series_windows(N, W, stride) == ref, (N, W, stride)
+
+
+def test_every_cuda_source_is_part_of_the_build():
+    """a .cu file that build.py does not list would silently stay out of libdeeprest_b200.so"""
+    import glob
+    from deeprest_b200 import build
+    here = os.path.dirname(os.path.abspath(build.__file__))
+    on_disk = sorted(os.path.basename(p) for p in glob.glob(os.path.join(here, "csrc", "*.cu")))
+    assert sorted(build.SOURCES) == on_disk
