@@ -64,6 +64,8 @@ SIGNATURES = {
     "dr_debug_read": (C.c_int, [_H, C.c_char_p, _FP, C.c_size_t]),
     "dr_tc_probe": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                               C.c_int32, C.c_int32, C.c_int32, _FP]),
+    "dr_tc_probe_mn": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32,
+                                 C.POINTER(C.c_uint32), _FP]),
     "dr_launch_count": (C.c_int64, [_H]),
     "dr_last_engine": (C.c_char_p, [_H]),
 }

@@ -80,12 +80,12 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wtc = nullptr; m->wtc_bytes = 0;
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
-    m->copy_stream = nullptr; m->stream2 = nullptr; m->d_tc_dbg = nullptr;
+    m->copy_stream = nullptr; m->stream2 = nullptr; m->d_tc_dbg = nullptr; m->tc_xdrop = 0;
     for (int i = 0; i < 4; ++i) { m->ws_S[i] = nullptr; m->ws_S_cap[i] = 0; }
     m->x_bstride = 0; m->d_dn = nullptr; m->dn_on = false; m->dn_clamp = 0.0f;
     for (int i = 0; i < 10; ++i) m->ev_pipe[i] = nullptr;
     m->d_xT = nullptr; m->xT_cap = 0; m->d_xtc = nullptr; m->xtc_cap = 0; m->ws_slot = 0;
-    for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; }
+    for (int i = 0; i < 4; ++i) { m->ws_xT[i] = nullptr; m->ws_xT_cap[i] = 0; m->ws_xtc[i] = nullptr; m->ws_xtc_cap[i] = 0; m->ws_p[i] = nullptr; m->ws_p_cap[i] = 0; m->ws_key[i] = nullptr; m->ws_tc[i] = false; }
     m->d_p = nullptr; m->p_cap = 0; m->p_live = false; m->d_himg = nullptr;
     m->d_xtc_tr = nullptr; m->xtc_tr_cap = 0; m->d_whT = nullptr; m->whT_cap = 0;
     m->d_S = nullptr; m->S_cap = 0; m->d_out = nullptr; m->out_cap = 0;
@@ -254,11 +254,28 @@ int dr_forward_local_dev(dr_model* m, const float* x, int32_t B, int32_t T, floa
     m->d_xT = m->ws_xT[slot]; m->xT_cap = m->ws_xT_cap[slot];
     m->d_xtc = m->ws_xtc[slot]; m->xtc_cap = m->ws_xtc_cap[slot];
     m->d_p = m->ws_p[slot]; m->p_cap = m->ws_p_cap[slot];
+    for (int i = 0; i < 4; ++i) if (m->ws_key[i] == S) m->ws_key[i] = nullptr;     // S_dev is being reused: older tickets for it are void
     rc = forward_local_slot(m, x, B, T, S, out_local);
+    m->ws_key[slot] = (rc == DR_OK) ? S : nullptr; m->ws_tc[slot] = m->p_live;
     m->ws_xT[slot] = m->d_xT; m->ws_xT_cap[slot] = m->xT_cap;
     m->ws_xtc[slot] = m->d_xtc; m->ws_xtc_cap[slot] = m->xtc_cap;
     m->ws_p[slot] = m->d_p; m->ws_p_cap[slot] = m->p_cap;
     return rc;
+}
+
+// The head phase consumes the own-expert partials its local phase left in one of the 4 workspace slots.  The pairing is
+// by the S_dev pointer (the caller passes the same buffer to both phases), so chunk pipelines may interleave
+// local(c0), local(c1), heads(c0), heads(c1); a heads call whose S_dev no live local call produced is an error, not a
+// silent read of another chunk's partials.
+static int bind_partials(dr_model* m, const float* S) {
+    if (m->M_loc == 0) return DR_OK;
+    for (int i = 0; i < 4; ++i)
+        if (m->ws_key[i] == S && S != nullptr) {
+            m->d_p = m->ws_p[i]; m->p_cap = m->ws_p_cap[i]; m->p_live = m->ws_tc[i];
+            return DR_OK;
+        }
+    return dr_fail(m, DR_ESTATE, "head phase without a matching dr_forward_local_dev: no live local phase wrote this S_dev "
+                                 "(at most 4 local phases may be in flight; each S_dev pairs one local with one heads call)");
 }
 
 int dr_forward_heads_dev(dr_model* m, const float* S, int32_t B, int32_t T, float* out_local) {
@@ -267,6 +284,8 @@ int dr_forward_heads_dev(dr_model* m, const float* S, int32_t B, int32_t T, floa
     if (rc != DR_OK) return rc;
     if (!S || !out_local) return dr_fail(m, DR_EINVAL, "null device pointer");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    rc = bind_partials(m, S);
+    if (rc != DR_OK) return rc;
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[2], m->stream));
     rc = m->p_live ? dr_launch_heads_tc(m, S, B, T, out_local) : dr_launch_heads(m, S, B, T, out_local);
@@ -280,6 +299,8 @@ int dr_forward_heads_p2p_dev(dr_model* m, const float* S, int32_t B, int32_t T, 
     int rc = check_shape(m, B, T);
     if (rc != DR_OK) return rc;
     if (!S || !out_ptrs || n_ptrs != m->cfg.world) return dr_fail(m, DR_EINVAL, "dr_forward_heads_p2p_dev: one destination per rank");
+    rc = bind_partials(m, S);
+    if (rc != DR_OK) return rc;
     if (!m->p_live) return dr_fail(m, DR_EUNSUPPORTED, "peer-write heads need the tcgen05 engine (input_size <= 64)");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     cudaEvent_t* ev = dr_prof_slot(m);
@@ -477,6 +498,7 @@ int dr_debug_read(dr_model* m, const char* what, float* host, size_t n) {
         DR_CUDA(m, cudaMemset(m->d_tc_dbg, 0, 32 * sizeof(unsigned long long)));
         return DR_OK;
     }
+    if (!strncmp(what, "tc_xdrop", 8) && what[8] >= '0' && what[8] <= '2' && !what[9]) { m->tc_xdrop = what[8] - '0'; return DR_OK; }
     if (!strcmp(what, "tc_timing")) {             // 18 counters as floats (cycles), see dr_gru_tc.cu
         if (!m->d_tc_dbg || n < 18) return dr_fail(m, DR_EINVAL, "tc_timing: enable with tc_timing_on first; needs 18 floats");
         unsigned long long h[32];

@@ -67,6 +67,8 @@ struct dr_model {
     // point at the slot of the call being issued
     float* ws_xT[4]; size_t ws_xT_cap[4]; void* ws_xtc[4]; size_t ws_xtc_cap[4]; int ws_slot;
     float* ws_p[4]; size_t ws_p_cap[4];
+    const float* ws_key[4]; bool ws_tc[4];   // the S_dev a slot was issued for, and whether that call ran on the tcgen05 engine:
+                                             // dr_forward_heads_dev finds its partials by the S pointer it is given
     uint8_t* d_himg;                // K2 weight images for the tcgen05 head GEMM (dr_head_tc.cu)
     float* d_p; size_t p_cap; bool p_live;   // own-expert head partials of the call being issued / consumed (tcgen05 engine)
     float* d_xT;   size_t xT_cap;   // x transposed to [T, Fp, Bp]            (FFMA engine)
@@ -83,6 +85,7 @@ struct dr_model {
     cudaStream_t own_stream;
     long long x_bstride;            // 0 = dense windows [B,T,F]; else floats between window starts (series mode, N1)
     float* d_dn; bool dn_on; float dn_clamp;   // optional output transform: scale[M_loc] | offset[M_loc] (N2)
+    int tc_xdrop;                   // precision probe: drop one split term of the x-part (dr_debug_read "tc_xdrop1"/"tc_xdrop2"/"tc_xdrop0")
     unsigned long long* d_tc_dbg;   // optional cycle breakdown of the tcgen05 kernel (dr_debug_read "tc_timing")
     cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
     cudaStream_t stream2;           // second compute stream of the pipelined host entry point

@@ -89,7 +89,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                  float* __restrict__ P,               // own-expert head partials [T][Bp/128][ceil(3M_loc/16)][dir*2+half][16][128]
                  int B, int T, int Bp, int M_loc, int ntiles,
                  unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */,
-                 TcTrainOut tr /* used only when kTrain */) {
+                 TcTrainOut tr /* used only when kTrain */,
+                 int xdrop /* 0: all three split terms of the x-part; 1 / 2: drop hi*lo / lo*hi (precision probe only) */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta = cluster_ctarank();
@@ -402,6 +403,7 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                     // x-part: (hi,hi) (hi,lo) (lo,hi);  A parts at xst + {0, kXTile}, B parts at wq + {0, kBlk}
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
+                        if (xdrop != 0 && term == xdrop) continue;  // xdrop is 0 (keep all), 1 or 2
                         const uint32_t ab = xst + (term == 2 ? kXTile : 0);
                         const uint32_t bb = wq + (term == 1 ? kBlk : 0);
 #pragma unroll
@@ -603,11 +605,11 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
     if (m->d_tc_dbg)
         dr_gru_tc_kernel<true, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg, TcTrainOut{});
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg, TcTrainOut{}, m->tc_xdrop);
     else
         dr_gru_tc_kernel<false, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{});
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{}, m->tc_xdrop);
     DR_CUDA(m, cudaGetLastError());
     if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
     m->launches += 2;
@@ -634,7 +636,7 @@ int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rz
     const int items = m->M_loc * 2 * ntiles;
     dr_gru_tc_kernel<false, true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
         reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc_tr), m->d_bias4, m->d_ct,
-        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows, lane_major});
+        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows, lane_major}, 0);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
     return DR_OK;

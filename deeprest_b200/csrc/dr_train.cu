@@ -489,6 +489,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     size_t rows = (size_t)T * Bm, E2 = (size_t)2 * Ml;
     if (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T) {
         int rc;
+        ws->cap_rows = 0; ws->cap_B = 0; ws->cap_T = 0;      // a failed allocation below leaves the workspace marked empty
         if ((rc = ws_alloc(m, &ws->xt, rows * F)) || (rc = ws_alloc(m, &ws->gi, E2 * rows * 4 * DR_H)) ||
             (rc = ws_alloc(m, &ws->rzn, E2 * rows * 3 * DR_H)) || (rc = ws_alloc(m, &ws->q, E2 * rows * DR_H)) ||
             (rc = ws_alloc(m, &ws->hs, E2 * rows * DR_H)) || (rc = ws_alloc(m, &ws->dhout, E2 * rows * DR_H)) ||
@@ -512,7 +513,9 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
     DR_CUDA(m, cudaMemsetAsync(m->d_loss, 0, sizeof(double), m->stream));
     ws->stage = TS_MB_BEGIN; ws->pass = 0; ws->mb = 0; ws->Bm = Bm; ws->n_mb = (B + Bm - 1) / Bm; ws->B = B; ws->T = T;
-    ws->x = x; ws->y = y; ws->mask = mask; ws->seed = seed; ws->lr = lr; ws->loss_dev = loss_dev; ws->out_dev = out_dev;
+    // the dropout draw is a pure function of (seed, element): mix the optimizer step in so that a loop calling
+    // train_step with a constant seed still draws a fresh mask every iteration (nn.Dropout does, qrnn.py:43)
+    ws->x = x; ws->y = y; ws->mask = mask; ws->seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(m->adam_step + 1); ws->lr = lr; ws->loss_dev = loss_dev; ws->out_dev = out_dev;
     return DR_OK;
 }
 
@@ -691,7 +694,20 @@ static int train_backward_mb(dr_model* m, dr_train_ws* ws, int b0, int bm) {
 }
 
 // kind: 0 = step finished, 1 = all-reduce(sum) `count` elements at `ptr` (dtype 0 = fp32, 1 = fp64) across the ranks, then call again
+static int train_advance_inner(dr_model* m, int* kind, void** ptr, long long* count, int* dtype);
+
+// any failure inside a step (a CUDA error after a launch, an allocation) abandons the step: the handle goes back to
+// TS_IDLE so that the next dr_train_begin is accepted instead of reporting "a training step is already in flight"
 int dr_train_advance_impl(dr_model* m, int* kind, void** ptr, long long* count, int* dtype) {
+    int rc = train_advance_inner(m, kind, ptr, count, dtype);
+    if (rc != DR_OK) {
+        dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
+        if (ws) ws->stage = TS_IDLE;
+    }
+    return rc;
+}
+
+static int train_advance_inner(dr_model* m, int* kind, void** ptr, long long* count, int* dtype) {
     dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
     if (!ws || ws->stage == TS_IDLE) return dr_fail(m, DR_ESTATE, "dr_train_advance without dr_train_begin");
     const int Ml = m->M_loc, M = m->cfg.M, T = ws->T, B = ws->B, F = m->cfg.F, pe = m->off.per_expert;

@@ -124,16 +124,12 @@ def state_dict_from_blob(blob: np.ndarray, M: int, F: int):
 
 
 def expert_range(rank: int, world: int, M: int):
-    """Contiguous expert shard owned by ``rank`` (shard by service ID).
-
-    Both metrics of a service (experts 2s, 2s+1) stay on one rank, so shards are
-    cut on even boundaries; the remainder goes to the low ranks.
-    """
-    if M % 2:
-        lo = (M * rank) // world
-        hi = (M * (rank + 1)) // world
-        return lo, hi
-    S = M // 2
-    lo = (S * rank) // world
-    hi = (S * (rank + 1)) // world
-    return 2 * lo, 2 * hi
+    """Contiguous expert shard owned by ``rank`` — the same rule the library applies (csrc/dr_api.cu::dr_create,
+    readable back through ``dr_local_experts``): equal shards of M/world experts, M divisible by world
+    (shard by service ID; with M = 2*services and an even M/world both metrics of a service share a rank)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    if M % world:
+        raise ValueError("num_metrics must be divisible by world (equal expert shards, as dr_create requires)")
+    per = M // world
+    return rank * per, (rank + 1) * per

@@ -108,11 +108,15 @@ int  dr_set_output_transform(dr_model* m, const float* scale_host, const float* 
  *   1. dr_forward_local_dev : local bi-GRUs.  Writes S_dev = sum over LOCAL experts of their GRU
  *      outputs (dr_s_elems(B,T) floats, stored k-group major [T][2H/4][round_up(B,128)][4]; the
  *      layout is opaque to the caller, an element-wise all-reduce is all it needs), and
- *      out_local_dev[B,T,M_loc,Q] = own-expert part of the heads.
+ *      out_local_dev[B,T,M_loc,Q] = own-expert part of the heads (FFMA engine; the tcgen05 engine keeps
+ *      its partials in a library workspace until step 3 writes out_local_dev).
  *   2. caller all-reduces (sum) S_dev across ranks (torch.distributed / NCCL).
  *   3. dr_forward_heads_dev : adds the cross-expert-mean term and bias into out_local_dev.
  *   4. caller all-gathers out_local into gathered[world][B,T,M_loc,Q];
- *      dr_interleave_dev reorders it to the reference layout out[B,T,M,Q] (qrnn.py:55). */
+ *      dr_interleave_dev reorders it to the reference layout out[B,T,M,Q] (qrnn.py:55).
+ *   Pairing: a heads call (3 or 3'+4') finds the own-expert partials of its chunk by the S_dev pointer it is given —
+ *   pass the SAME S_dev buffer to step 1 and step 3.  Up to 4 local phases may be in flight (different S_dev buffers,
+ *   any streams, any interleaving); a heads call with an S_dev no live local phase produced returns DR_ESTATE. */
 int64_t dr_s_elems(int32_t B, int32_t T);     /* floats in S_dev for a [B,T] call */
 int  dr_forward_local_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T,
                           float* S_dev, float* out_local_dev);
@@ -179,6 +183,11 @@ int  dr_profile_read(dr_model* m, int32_t* n_forwards, float* gru_ms_sum, float*
  * csrc/dr_tc_probe.cu). variant bit0: A from TMEM, bit1: cta_group::2. Host pointers. */
 int  dr_tc_probe(int32_t variant, const void* a_host, size_t a_bytes, const void* b_host, size_t b_bytes,
                  int32_t N, int32_t K, int32_t flags, float* d_out_host);
+/* same for operands in the MN-major SW128 canonical layout (reduced index slowest), the form the bf16 weight-gradient
+ * kernel consumes: D[128 x N] = sum_k A[k][m] B[k][n].  params: 8 x uint32 {a_lbo, a_sbo, a_kstep, b_lbo, b_sbo, b_kstep,
+ * a_mn, b_mn} (bytes / major bits); a, b: ready shared-memory images.  See csrc/dr_tc_probe.cu. */
+int  dr_tc_probe_mn(const void* a_host, size_t a_bytes, const void* b_host, size_t b_bytes, int32_t N, int32_t K,
+                    const uint32_t* params, float* d_out_host);
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 int64_t dr_launch_count(const dr_model* m);
 /* name of the GRU engine the last forward used: "ffma" or "tcgen05" */

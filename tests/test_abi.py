@@ -87,11 +87,12 @@ def test_generator_is_counter_based():
 
 
 def test_expert_sharding_plan():
-    for M, world in [(2048, 8), (128, 1), (1024, 8), (6, 3)]:
+    """layout.expert_range is the library's rule (dr_create: equal contiguous shards, M % world == 0)."""
+    for M, world in [(2048, 8), (128, 1), (1024, 8), (6, 3), (6, 2)]:
         spans = [layout.expert_range(r, world, M) for r in range(world)]
-        assert spans[0][0] == 0 and spans[-1][1] == M
-        for (a, b), (c, d) in zip(spans, spans[1:]):
-            assert b == c and a % 2 == 0
+        assert spans == [(r * (M // world), (r + 1) * (M // world)) for r in range(world)]
+    with pytest.raises(ValueError):
+        layout.expert_range(0, 4, 6)
 
 
 def test_series_window_count_matches_reference_sliding_window():

@@ -92,3 +92,65 @@ def test_tcgen05_tile(variant, name, N, K):
         np.save(f"gpurun_out/probe_v{variant}_N{N}_K{K}_out.npy", out)
         np.save(f"gpurun_out/probe_v{variant}_N{N}_K{K}_ref.npy", ref)
         pytest.fail(f"{name} N={N} K={K}: max err {err:.3e}; " + "; ".join(hints))
+
+
+def mn_image(bits, nblk_pad=None):
+    """[K, MN] uint16 (MN contiguous per reduced index k) -> byte image [MN/64 blocks][K/8 groups][8 rows x 128 B]:
+    the MN-major SW128 canonical layout (16-byte chunks of a 128-byte row XOR-swizzled by k & 7)."""
+    K, MN = bits.shape
+    nb = (MN + 63) // 64
+    pad = np.zeros((K, nb * 64), np.uint16)
+    pad[:, :MN] = bits
+    img = np.zeros((nb, K // 8, 8, 64), np.uint16)
+    k = np.arange(K)
+    for blk in range(nb):
+        for ch in range(8):
+            src = pad[:, blk * 64 + ch * 8: blk * 64 + ch * 8 + 8]              # [K, 8]
+            dst_ch = ch ^ (k & 7)
+            for kk in range(K):
+                img[blk, kk // 8, kk % 8, dst_ch[kk] * 8: dst_ch[kk] * 8 + 8] = src[kk]
+    return img
+
+
+def run_probe_mn(A, B, params=None):
+    """A [K,128], B [K,N] fp32 -> D[128,N] = A^T B on the tensor core with both operands MN-major."""
+    lib = _lib.load()
+    K, N = B.shape
+    a_bits, a_val = bf16_round(A)
+    b_bits, b_val = bf16_round(B)
+    a_img = np.ascontiguousarray(mn_image(a_bits))
+    b_img = np.ascontiguousarray(mn_image(b_bits))
+    blk = (K // 8) * 1024                        # bytes between 64-element MN blocks
+    if params is None:                           # hypothesis H1: LBO = MN-block stride, SBO = 8-k group stride, 2 groups per K=16
+        params = [blk, 1024, 2048, blk, 1024, 2048, 1, 1]
+    prm = (C.c_uint32 * 8)(*params)
+    out = np.zeros((128, N), np.float32)
+    rc = lib.dr_tc_probe_mn(a_img.ctypes.data, a_img.nbytes, b_img.ctypes.data, b_img.nbytes, N, K, prm,
+                            out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0, lib.dr_last_error(None)
+    ref = a_val.astype(np.float64).T @ b_val.astype(np.float64)
+    return out, ref
+
+
+@pytest.mark.parametrize("N,K", [(128, 64), (208, 64), (80, 128), (16, 32)])
+def test_tcgen05_tile_mn_major(N, K):
+    rng = np.random.default_rng(N + K)
+    A = rng.standard_normal((K, 128)).astype(np.float32)
+    B = rng.standard_normal((K, N)).astype(np.float32)
+    out, ref = run_probe_mn(A, B)
+    err = np.abs(out - ref).max()
+    print(f"MN-major N={N} K={K}: max err {err:.3e}")
+    if err > 1e-3:
+        blk = (K // 8) * 1024
+        hints = []
+        for name, prm in [("LBO/SBO swapped", [1024, blk, 2048, 1024, blk, 2048, 1, 1]),
+                          ("kstep = 1 group", [blk, 1024, 1024, blk, 1024, 1024, 1, 1]),
+                          ("major bits off", [blk, 1024, 2048, blk, 1024, 2048, 0, 0])]:
+            try:
+                o2, _ = run_probe_mn(A, B, prm)
+                hints.append(f"{name} -> {np.abs(o2 - ref).max():.3e}")
+            except AssertionError as exc:
+                hints.append(f"{name} -> {exc}")
+        np.save(f"gpurun_out/probe_mn_N{N}_K{K}_out.npy", out)
+        np.save(f"gpurun_out/probe_mn_N{N}_K{K}_ref.npy", ref)
+        pytest.fail(f"MN-major N={N} K={K}: max err {err:.3e}; " + "; ".join(hints))

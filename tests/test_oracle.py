@@ -139,3 +139,17 @@ def test_fp64_grads_match_finite_differences():
         lq = oracle.quantile_loss(oracle.forward(q, x, M, F, np.float64, dm), y, dtype=np.float64)
         fd = (lp - lq) / (2 * eps)
         assert abs(fd - g[idx]) < 1e-6 * max(1.0, abs(fd)), (name, fd, g[idx])
+
+
+def test_product_normalization_minmax_matches_reference_golden():
+    """The product's own host helpers (estimator.sliding_window / QuantileRNN.normalization_minmax; utils.py:4-5,
+    qrnn.py:69-75) against the reference-minted G8 — not only the oracle's copies."""
+    from deeprest_b200.estimator import QuantileRNN, sliding_window
+    g = np.load(os.path.join(GOLDEN_DIR, "g8_window_norm.npz"))
+    win = sliding_window(g["ts"], int(g["window"]))
+    assert win.shape == g["win"].shape and np.array_equal(win, g["win"])
+    got, lo, hi = QuantileRNN.normalization_minmax(win.copy(), int(g["split"]))
+    assert np.array_equal(got, g["norm"]) and lo == g["lo"] and hi == g["hi"]
+    const = np.full((7, 3), 2.5)
+    same, lo, hi = QuantileRNN.normalization_minmax(const, 4)          # span == 0: the reference returns M itself
+    assert same is const and lo == 2.5 and hi == 2.5
