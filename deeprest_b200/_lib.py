@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libdeeprest_b200.so")
 
 DR_OK, DR_EINVAL, DR_ECUDA, DR_ENOMEM, DR_ESTATE, DR_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 ENGINE_AUTO, ENGINE_FFMA, ENGINE_TC = 0, 1, 2
+DTYPES = {"fp32": 0, "f32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
 ENGINES = {"auto": ENGINE_AUTO, "ffma": ENGINE_FFMA, "tcgen05": ENGINE_TC, "tc": ENGINE_TC}
 
 
@@ -22,6 +23,7 @@ class DrConfig(C.Structure):
         ("F", C.c_int32), ("M", C.c_int32), ("H", C.c_int32), ("Q", C.c_int32),
         ("quantiles", C.c_float * 8), ("dropout_p", C.c_float),
         ("engine", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("dtype", C.c_int32),
     ]
 
 

@@ -49,6 +49,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return dr_fail(nullptr, DR_EINVAL, "bad rank/world");
     if (cfg->M % cfg->world) return dr_fail(nullptr, DR_EINVAL, "num_metrics must be divisible by world (equal expert shards)");
     if (cfg->engine < DR_ENGINE_AUTO || cfg->engine > DR_ENGINE_TC) return dr_fail(nullptr, DR_EINVAL, "bad engine");
+    if (cfg->dtype != DR_DTYPE_F32 && cfg->dtype != DR_DTYPE_BF16) return dr_fail(nullptr, DR_EINVAL, "bad dtype");
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);

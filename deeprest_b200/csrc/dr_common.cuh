@@ -145,6 +145,18 @@ int dr_launch_wgrad_tc(dr_model* m, int ndir, const float* const* A, long long l
 // backward recurrence of one micro-batch on the tensor-core engine (dr_gru_bwd_tc.cu): gate adjoints + dh chain, in place
 int dr_launch_gru_bwd_tc(dr_model* m, const float* rzn, const float* q, const float* hs, const float* dhout, float* g4,
                          long long dir_rows, long long dho_dir_rows, int Bm, int T, float inv_n, int in_lane_major);
+// bf16 training engine (dr_gru_tc16.cu, dr_gru_bwd16.cu, dr_wgrad16.cu; layout in dr_t16.cuh)
+size_t dr_t16_wimg_bytes(int M_loc);
+size_t dr_t16_whT_bytes(int M_loc);
+int dr_t16_pack_weights(dr_model* m, uint8_t* wimg);
+int dr_t16_pack_whT(dr_model* m, uint8_t* img);
+int dr_t16_pack_x(dr_model* m, const float* x_mb, int Bm, int T, uint8_t* ximg);
+int dr_launch_gru_tc16(dr_model* m, const uint8_t* wimg, const uint8_t* ximg, int Bm, int T, float* S, float* P,
+                       uint8_t* gate, uint8_t* himg, const uint8_t* mask, uint64_t seed, int b0, int Bfull);
+int dr_launch_gru_bwd16(dr_model* m, const uint8_t* whT, uint8_t* gate, const uint8_t* himg, const float* dy, const float* gbar,
+                        int Bm, int T, const uint8_t* mask, uint64_t seed, int b0, int Bfull);
+int dr_launch_wgrad16(dr_model* m, const uint8_t* gate, const uint8_t* himg, const uint8_t* ximg, const uint8_t* zero,
+                      float* P, int Bm, int T);
 // dr_train.cu
 int dr_train_step_impl(dr_model* m, const float* x, const float* y, int B, int T, const uint8_t* mask, uint64_t seed,
                        float lr, float* loss_dev, float* out_dev);

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include "dr_common.cuh"
+#include "dr_t16.cuh"
 
 namespace {
 
@@ -426,6 +427,40 @@ __global__ void dr_adam_kernel(float* __restrict__ w, const float* __restrict__ 
 
 __global__ void dr_finish_loss_kernel(const double* acc, double inv_n, float* loss) { *loss = (float)(*acc * inv_n); }
 
+// bf16 engine: head weight gradients from the h images.  U[e][q][k] = sum_{t,b} dy r~ ; V = sum dy S ; db = sum dy
+// (dC = U, dA = (V - U)/(M-1); qrnn.py:46-54 differentiated).  grid (M_loc, row chunks), 256 threads = column k of [fwd | rev];
+// rows are walked window-fastest so that a warp's h reads stay inside one 128-byte image row and S lines are reused from L1.
+__global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ S, const float* __restrict__ dy,
+                                                              drt16::Drop drop, float* __restrict__ gblob, int off_hw, int off_hb, int pe, float inv_m1,
+                                                              int M_loc, int e_lo, int Bfull, int b0, int Bm, int T, int rows_per_chunk) {
+    const int e = blockIdx.x, k = threadIdx.x;
+    const int d = k >> 7, j = k & 127;
+    const int ntiles = (Bm + 127) >> 7, Bp = ntiles * 128;
+    const size_t rows = (size_t)T * Bm;
+    size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
+    if (r1 > rows) r1 = rows;
+    float u[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f};
+    for (size_t r = r0; r < r1; ++r) {
+        const int t = (int)(r / Bm), b = (int)(r % Bm);
+        const uint8_t* hrow = himg + drt16::blk_index(d, e, t, b >> 7, M_loc, T, ntiles) * drt16::kHImg + (size_t)(j >> 6) * drt16::kColBlk +
+                              drt16::img_off(b & 127, (j & 63) >> 3) + (j & 7) * 2;
+        const float h = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(hrow)) << 16);
+        const size_t midx = (((size_t)(e_lo + e) * Bfull + b0 + b) * T + t) * DR_2H + k;
+        const float rt = drt16::keep1(drop, midx) ? h * drop.inv_keep : 0.0f;
+        const float s = S[(((size_t)t * 64 + (k >> 2)) * Bp + b) * 4 + (k & 3)];
+        const float* dd = dy + (((size_t)b * T + t) * M_loc + e) * DR_Q;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { const float g = dd[q]; u[q] = fmaf(g, rt, u[q]); v[q] = fmaf(g, s, v[q]); if (k == 0) sb[q] += g; }
+    }
+    float* hw = gblob + (size_t)e * pe + off_hw;      // [Q][4H]: cols 0..2H-1 = A (mean part), 2H.. = C (own part)
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        atomicAdd(hw + (size_t)q * 4 * DR_H + DR_2H + k, u[q]);
+        atomicAdd(hw + (size_t)q * 4 * DR_H + k, (v[q] - u[q]) * inv_m1);
+        if (k == 0) atomicAdd(gblob + (size_t)e * pe + off_hb + q, sb[q]);
+    }
+}
+
 inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 int gemm(dr_model* m, const Gemm& g, int batch) {
@@ -446,11 +481,16 @@ int gemm(dr_model* m, const Gemm& g, int batch) {
 // head adjoint G-bar before the backward of a micro-batch).  The host performs that all-reduce on the returned
 // device buffer and calls advance again (torch.distributed in the Python host; NCCL in a C/Go host).  With
 // world == 1 no request is ever produced and dr_train_step simply drives the machine to completion.
-enum { TS_IDLE = 0, TS_MB_BEGIN, TS_AFTER_S, TS_AFTER_LOSS, TS_AFTER_G, TS_FINISH };
+enum { TS_IDLE = 0, TS_MB_BEGIN, TS_AFTER_S, TS_AFTER_LOSS, TS_AFTER_G, TS_FINISH,
+       T16_MB_BEGIN, T16_AFTER_S, T16_AFTER_G, T16_AFTER_LOSS };     // bf16 engine: one pass per micro-batch
 
 struct dr_train_ws {
     float *xt, *gi, *rzn, *q, *hs, *dhout, *gh, *dhc, *S, *gbar, *dy, *P, *dmask;
     size_t cap_rows; int cap_B; int cap_T;
+    // bf16 engine (dr_config.dtype == DR_DTYPE_BF16): operand images instead of fp32 activation rows (dr_t16.cuh)
+    uint8_t *w16, *whT16, *x16, *gate16, *h16, *zero16;
+    float *S16, *P16, *dy16, *gbar16, *Px16;
+    int cap16_tiles, cap16_T;
     // state of the step in flight
     int stage, pass, mb, n_mb, Bm, B, T;
     const float *x, *y; const uint8_t* mask; uint64_t seed; float lr; float* loss_dev; float* out_dev;
@@ -460,6 +500,69 @@ static int ws_alloc(dr_model* m, float** p, size_t n) {
     if (*p) { cudaFree(*p); *p = nullptr; }
     cudaError_t e = cudaMalloc((void**)p, (n ? n : 4) * sizeof(float));
     if (e != cudaSuccess) return dr_cuda_fail(m, e, "cudaMalloc(training workspace)");
+    return DR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bf16 engine (dr_config.dtype == DR_DTYPE_BF16): single-pass bf16 tensor-core kernels, bf16 activation images
+// (csrc/dr_gru_tc16.cu, dr_gru_bwd16.cu, dr_wgrad16.cu, layout in dr_t16.cuh).  One pass per micro-batch of whole
+// 128-window tiles:   x image -> train-mode forward (dropout, S, head partials, saved images) -> [S all-reduce] -> heads
+// (the inference K2) -> pinball-loss gradient of these windows -> G-bar GEMM -> [G-bar all-reduce] -> reverse chain ->
+// weight-gradient GEMM -> head gradients.   The loss gradient of a window needs only that window's forecasts (the 1/(M·B·T)
+// of the mean is a constant), so no forward is ever recomputed; the loss VALUE is summed across micro-batches.
+static int ws16_alloc(dr_model* m, void** p, size_t bytes) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return dr_cuda_fail(m, e, "cudaMalloc(bf16 training workspace)");
+    return DR_OK;
+}
+
+static int train16_begin(dr_model* m, dr_train_ws* ws, int B, int T) {
+    const int F = m->cfg.F, Ml = m->M_loc;
+    if (F > 64) return dr_fail(m, DR_EUNSUPPORTED, "bf16 training engine: input_size must be <= 64 (one 64-wide K block of x)");
+    if (!m->d_himg && Ml) return dr_fail(m, DR_ESTATE, "bf16 training engine: head images missing (load weights first)");
+    const int tiles_all = (B + 127) / 128;
+    const size_t ngrp = (size_t)(Ml * DR_Q + 15) / 16;
+    // bytes per 128-window tile of a micro-batch
+    const size_t per_tile = (size_t)2 * Ml * T * (drt16::kGateImg + drt16::kHImg) + (size_t)T * drt16::kColBlk +
+                            (size_t)T * DR_2H * 128 * 4 /* S */ + (size_t)T * ngrp * 4 * 16 * 128 * 4 /* P */ +
+                            (size_t)128 * T * Ml * DR_Q * 4 /* dy */ + (size_t)128 * T * DR_2H * 4 /* gbar */;
+    size_t budget = (size_t)24 << 30;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            size_t held = (size_t)ws->cap16_tiles * per_tile;
+            budget = std::max<size_t>((size_t)4 << 30, (free_b + held) * 7 / 10);
+        }
+    }
+    int mb_tiles = (int)std::min<size_t>((size_t)tiles_all, std::max<size_t>(1, budget / std::max<size_t>(per_tile, 1)));
+    if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) mb_tiles = std::min(tiles_all, (v + 127) / 128); }   // test hook
+    const int Bm = std::min(B, mb_tiles * 128);
+    if (ws->cap16_tiles < mb_tiles || ws->cap16_T != T) {
+        ws->cap16_tiles = 0; ws->cap16_T = 0;
+        const size_t nt = (size_t)mb_tiles;
+        int rc;
+        if ((rc = ws16_alloc(m, (void**)&ws->w16, dr_t16_wimg_bytes(Ml))) || (rc = ws16_alloc(m, (void**)&ws->whT16, dr_t16_whT_bytes(Ml))) ||
+            (rc = ws16_alloc(m, (void**)&ws->x16, (size_t)T * nt * drt16::kColBlk)) ||
+            (rc = ws16_alloc(m, (void**)&ws->gate16, (size_t)2 * Ml * T * nt * drt16::kGateImg)) ||
+            (rc = ws16_alloc(m, (void**)&ws->h16, (size_t)2 * Ml * T * nt * drt16::kHImg)) ||
+            (rc = ws16_alloc(m, (void**)&ws->zero16, drt16::kColBlk)) ||
+            (rc = ws16_alloc(m, (void**)&ws->S16, (size_t)T * DR_2H * nt * 128 * sizeof(float))) ||
+            (rc = ws16_alloc(m, (void**)&ws->P16, (size_t)T * nt * ngrp * 4 * 16 * 128 * sizeof(float))) ||
+            (rc = ws16_alloc(m, (void**)&ws->dy16, (size_t)nt * 128 * T * Ml * DR_Q * sizeof(float))) ||
+            (rc = ws16_alloc(m, (void**)&ws->gbar16, (size_t)nt * 128 * T * DR_2H * sizeof(float))) ||
+            (rc = ws16_alloc(m, (void**)&ws->Px16, (size_t)2 * Ml * 3 * DR_H * F * sizeof(float))) ||
+            (rc = ws_alloc(m, &ws->dmask, (size_t)Ml * F)))
+            return rc;
+        DR_CUDA(m, cudaMemsetAsync(ws->zero16, 0, drt16::kColBlk, m->stream));
+        ws->cap16_tiles = mb_tiles; ws->cap16_T = T;
+    }
+    DR_CUDA(m, cudaMemsetAsync(ws->Px16, 0, (size_t)2 * Ml * 3 * DR_H * F * sizeof(float), m->stream));
+    DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
+    int rc = dr_t16_pack_weights(m, ws->w16);
+    if (rc) return rc;
+    if ((rc = dr_t16_pack_whT(m, ws->whT16))) return rc;
+    ws->stage = T16_MB_BEGIN; ws->pass = 0; ws->mb = 0; ws->Bm = Bm; ws->n_mb = (B + Bm - 1) / Bm;
     return DR_OK;
 }
 
@@ -486,8 +589,12 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
     if (!ws) { ws = new dr_train_ws(); memset(ws, 0, sizeof(*ws)); m->train_ws = ws; }
     if (ws->stage != TS_IDLE) return dr_fail(m, DR_ESTATE, "a training step is already in flight on this handle");
+    const bool bf16 = m->cfg.dtype == DR_DTYPE_BF16;
+    if (bf16 && m->cfg.engine == DR_ENGINE_FFMA)
+        return dr_fail(m, DR_EINVAL, "dtype bf16 selects the single-pass tensor-core training engine; it cannot be combined with engine FFMA");
     size_t rows = (size_t)T * Bm, E2 = (size_t)2 * Ml;
-    if (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T) {
+    if (bf16) rows = 0;                                 // the fp32 activation rows are not used
+    if (!bf16 && (ws->cap_rows < rows || ws->cap_B < B || ws->cap_T != T)) {
         int rc;
         ws->cap_rows = 0; ws->cap_B = 0; ws->cap_T = 0;      // a failed allocation below leaves the workspace marked empty
         if ((rc = ws_alloc(m, &ws->xt, rows * F)) || (rc = ws_alloc(m, &ws->gi, E2 * rows * 4 * DR_H)) ||
@@ -510,9 +617,13 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
         m->adam_step = 0;
     }
     DR_CUDA(m, cudaMemsetAsync(m->d_grad, 0, nblob * sizeof(float), m->stream));
-    DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
+    if (!bf16) DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
     DR_CUDA(m, cudaMemsetAsync(m->d_loss, 0, sizeof(double), m->stream));
     ws->stage = TS_MB_BEGIN; ws->pass = 0; ws->mb = 0; ws->Bm = Bm; ws->n_mb = (B + Bm - 1) / Bm; ws->B = B; ws->T = T;
+    if (bf16) {
+        int rc = train16_begin(m, ws, B, T);
+        if (rc) { ws->stage = TS_IDLE; return rc; }
+    }
     // the dropout draw is a pure function of (seed, element): mix the optimizer step in so that a loop calling
     // train_step with a constant seed still draws a fresh mask every iteration (nn.Dropout does, qrnn.py:43)
     ws->x = x; ws->y = y; ws->mask = mask; ws->seed = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(m->adam_step + 1); ws->lr = lr; ws->loss_dev = loss_dev; ws->out_dev = out_dev;
@@ -770,6 +881,77 @@ static int train_advance_inner(dr_model* m, int* kind, void** ptr, long long* co
             if (ws->mb + 1 < ws->n_mb) { ws->mb += 1; ws->stage = TS_MB_BEGIN; } else ws->stage = TS_FINISH;
             break;
         }
+        // ---------------- bf16 engine: one pass per micro-batch ----------------
+        case T16_MB_BEGIN: {
+            int rc = dr_t16_pack_x(m, ws->x + (size_t)b0 * T * F, bm, T, ws->x16);
+            if (rc) return rc;
+            rc = dr_launch_gru_tc16(m, ws->w16, ws->x16, bm, T, ws->S16, ws->P16, ws->gate16, ws->h16, ws->mask, ws->seed, b0, B);
+            if (rc) return rc;
+            m->last_engine = "tcgen05-bf16";
+            ws->stage = T16_AFTER_S;
+            if (sharded) { *kind = 1; *ptr = ws->S16; *count = (long long)dr_s_floats(bm, T); *dtype = 0; return DR_OK; }
+            break;
+        }
+        case T16_AFTER_S: {
+            // heads: the inference head kernel on the (complete) S and this micro-batch's own-expert partials; the optional
+            // inference output transform is not part of the training graph
+            float* out_mb = ws->out_dev + (size_t)b0 * T * Ml * DR_Q;
+            float* keep_p = m->d_p; const bool keep_dn = m->dn_on;
+            m->d_p = ws->P16; m->dn_on = false;
+            int rc = dr_launch_heads_tc(m, ws->S16, bm, T, out_mb);
+            m->d_p = keep_p; m->dn_on = keep_dn;
+            if (rc) return rc;
+            const size_t n_rm = (size_t)bm * T * Ml;
+            if (n_rm) {
+                unsigned blocks = std::max(1u, std::min<unsigned>(nblk(n_rm), 148u * 8u));
+                dr_loss_grad_kernel<<<blocks, 256, 0, st>>>(out_mb, ws->y + (size_t)b0 * T * Ml, ws->dy16, n_rm, m->cfg.quantiles[0],
+                                                             m->cfg.quantiles[1], m->cfg.quantiles[2], inv_n, acc);
+                DR_CUDA(m, cudaGetLastError());
+                m->launches += 1;
+            }
+            // G-bar[(b,t)][k] = sum_{e,q} Abar[e][q][k] dy[b,t,e,q]: one fp32 GEMM [bm*T x 3M_loc] x [3M_loc x 2H]
+            if (Ml) {
+                Gemm gg{ws->dy16, m->d_abar, ws->gbar16, (int)((size_t)bm * T), DR_2H, Ml * DR_Q,
+                        (long)Ml * DR_Q, 1, DR_2H, 1, DR_2H, 1, 0, 0, 0, 0.0f};
+                rc = gemm(m, gg, 1);
+                if (rc) return rc;
+            } else {
+                DR_CUDA(m, cudaMemsetAsync(ws->gbar16, 0, (size_t)bm * T * DR_2H * sizeof(float), st));
+            }
+            ws->stage = T16_AFTER_G;
+            if (sharded) { *kind = 1; *ptr = ws->gbar16; *count = (long long)((size_t)bm * T * DR_2H); *dtype = 0; return DR_OK; }
+            break;
+        }
+        case T16_AFTER_G: {
+            int rc = dr_launch_gru_bwd16(m, ws->whT16, ws->gate16, ws->h16, ws->dy16, ws->gbar16, bm, T, ws->mask, ws->seed, b0, B);
+            if (rc) return rc;
+            rc = dr_launch_wgrad16(m, ws->gate16, ws->h16, ws->x16, ws->zero16, ws->Px16, bm, T);
+            if (rc) return rc;
+            if (Ml) {
+                const int chunk = 2048;
+                dim3 grid(Ml, (unsigned)(((size_t)T * bm + chunk - 1) / chunk));
+                drt16::Drop dp;
+                dp.mask = ws->mask; dp.seed = ws->seed; dp.inv_keep = 1.0f / (1.0f - p); dp.thr16 = (uint32_t)(p * 65536.0f + 0.5f);
+                dr_head_grad16_kernel<<<grid, 256, 0, st>>>(ws->h16, ws->S16, ws->dy16, dp, m->d_grad, m->off.head_w, m->off.head_b, pe,
+                                                            1.0f / (float)(M - 1), Ml, m->e_lo, B, b0, bm, T, chunk);
+                DR_CUDA(m, cudaGetLastError());
+                m->launches += 1;
+            }
+            if (ws->mb + 1 < ws->n_mb) { ws->mb += 1; ws->stage = T16_MB_BEGIN; break; }
+            ws->stage = T16_AFTER_LOSS;
+            if (sharded) { *kind = 1; *ptr = acc; *count = 1; *dtype = 1; return DR_OK; }
+            break;
+        }
+        case T16_AFTER_LOSS: {
+            dr_finish_loss_kernel<<<1, 1, 0, st>>>(acc, (double)inv_n, ws->loss_dev);
+            for (int d = 0; d < 2 && Ml; ++d)
+                dr_wih_grad_kernel<<<Ml, 128, 0, st>>>(ws->Px16 + (size_t)d * Ml * 3 * DR_H * F, m->d_blob, m->d_mask, m->d_grad, ws->dmask,
+                                                       m->off.w_ih[d], pe, F);
+            DR_CUDA(m, cudaGetLastError());
+            m->launches += 3;
+            ws->stage = TS_FINISH;
+            break;
+        }
         case TS_FINISH: {
             size_t nblob = (size_t)Ml * pe;
             if (Ml) dr_mask_bwd_kernel<<<Ml, DR_H, F * sizeof(float), st>>>(m->d_blob, m->off, F, m->d_mask, ws->dmask, m->d_grad);
@@ -876,6 +1058,8 @@ void dr_train_free(dr_model* m) {
     if (!ws) return;
     float* ptrs[] = {ws->xt, ws->gi, ws->rzn, ws->q, ws->hs, ws->dhout, ws->gh, ws->dhc, ws->S, ws->gbar, ws->dy, ws->P, ws->dmask};
     for (float* p : ptrs) if (p) cudaFree(p);
+    void* p16[] = {ws->w16, ws->whT16, ws->x16, ws->gate16, ws->h16, ws->zero16, ws->S16, ws->P16, ws->dy16, ws->gbar16, ws->Px16};
+    for (void* p : p16) if (p) cudaFree(p);
     delete ws;
     m->train_ws = nullptr;
 }

@@ -43,7 +43,7 @@ def _is_torch(t):
 class QuantileRNN:
     def __init__(self, input_size, num_metrics, hidden_layer_size=128, num_layers=1, bidirectional=True,
                  quantiles=(.05, .50, .95), dropout=0.50, *, engine="auto", device=None,
-                 process_group=None, rank=None, world=None):
+                 process_group=None, rank=None, world=None, dtype="fp32"):
         if hidden_layer_size != layout.H or num_layers != 1 or not bidirectional:
             raise NotImplementedError(
                 "libdeeprest_b200 implements the reference defaults only: hidden_layer_size=128, "
@@ -79,7 +79,7 @@ class QuantileRNN:
         self._lib = _lib.load()
         cfg = _lib.DrConfig(F=self.input_size, M=self.num_metrics, H=layout.H, Q=layout.Q,
                             dropout_p=self.dropout_p, engine=_lib.ENGINES[engine], device=self.device,
-                            rank=self.rank, world=self.world)
+                            rank=self.rank, world=self.world, dtype=_lib.DTYPES[dtype])
         for i, q in enumerate(self.quantiles):
             cfg.quantiles[i] = q
         self._h = C.c_void_p()

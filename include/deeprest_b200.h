@@ -47,6 +47,10 @@ extern "C" {
 #define DR_ENGINE_FFMA  1    /* fp32 CUDA-core kernel (exact fp32 accumulate)               */
 #define DR_ENGINE_TC    2    /* tcgen05 tensor-core kernels, split-fp16 (3-pass) operands   */
 
+/* arithmetic of the TRAINING step (dr_config.dtype); inference always runs the fp32-parity split-fp16 engine */
+#define DR_DTYPE_F32    0    /* split-fp16 (3 tensor passes) or FFMA: every gradient inside the fp32 parity bounds          */
+#define DR_DTYPE_BF16   1    /* single-pass bf16 operands, fp32 accumulate, bf16-stored activations (BASELINE configs[2],[4]) */
+
 typedef struct dr_model dr_model;
 
 /* Mirrors QuantileRNN.__init__(input_size, num_metrics, hidden_layer_size=128, num_layers=1,
@@ -62,6 +66,7 @@ typedef struct dr_config {
     int32_t engine;         /* DR_ENGINE_*                                                  */
     int32_t device;         /* CUDA ordinal                                                 */
     int32_t rank, world;    /* expert shard: this handle owns experts [rank*M/world, ...)   */
+    int32_t dtype;          /* DR_DTYPE_*: arithmetic of dr_train_step          */
 } dr_config;
 
 /* ---- lifecycle: replaces QuantileRNN(...).to(device)  (estimate.py:60) ---- */

@@ -29,8 +29,17 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_config_struct_matches_header():
-    # int32 F,M,H,Q; float[8]; float; int32 engine,device,rank,world
-    assert C.sizeof(_lib.DrConfig) == 4 * 4 + 8 * 4 + 4 + 4 * 4
+    # int32 F,M,H,Q; float[8]; float; int32 engine,device,rank,world,dtype — field order as in the header
+    assert C.sizeof(_lib.DrConfig) == 4 * 4 + 8 * 4 + 4 + 5 * 4
+    text = open(os.path.join(ROOT, "include", "deeprest_b200.h")).read()
+    body = re.search(r"typedef struct dr_config \{(.*?)\} dr_config;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:                                           # "int32_t rank, world" / "float quantiles[8]"
+            names += [re.sub(r"\[\d+\]", "", n).strip() for n in decl.split(None, 1)[1].split(",")]
+    assert names == [f[0] for f in _lib.DrConfig._fields_], names
 
 
 def test_no_cpu_fallback():
