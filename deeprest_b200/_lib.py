@@ -54,6 +54,11 @@ SIGNATURES = {
     "dr_forward_heads_p2p_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int64]),
     "dr_scatter_forecasts_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int64]),
     "dr_interleave_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dr_comm_arena_bytes": (C.c_int64, [_H, C.c_int32, C.c_int32]),
+    "dr_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dr_comm_attach": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dr_forward_sharded_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "dr_forward_sharded": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dr_quantile_loss": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_quantile_loss_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "dr_train_step": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_float, _FP]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeeprest_b200.so")
 SOURCES = ["dr_api.cu", "dr_prep.cu", "dr_gru_ffma.cu", "dr_gru_tc.cu", "dr_tc_probe.cu", "dr_head.cu", "dr_head_tc.cu", "dr_train.cu", "dr_gru_bwd_tc.cu", "dr_wgrad_tc.cu",
-           "dr_gru_tc16.cu", "dr_gru_bwd16.cu", "dr_wgrad16.cu"]
+           "dr_gru_tc16.cu", "dr_gru_bwd16.cu", "dr_wgrad16.cu", "dr_comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -82,6 +82,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
     m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
     m->copy_stream = nullptr; m->stream2 = nullptr; m->d_tc_dbg = nullptr; m->tc_xdrop = 0;
+    m->tile_count = nullptr; m->tile_flag = nullptr; m->tile_value = 0; m->comm = nullptr;
     for (int i = 0; i < 4; ++i) { m->ws_S[i] = nullptr; m->ws_S_cap[i] = 0; }
     m->x_bstride = 0; m->d_dn = nullptr; m->dn_on = false; m->dn_clamp = 0.0f;
     for (int i = 0; i < 10; ++i) m->ev_pipe[i] = nullptr;
@@ -121,6 +122,7 @@ void dr_destroy(dr_model* m) {
     cudaSetDevice(m->cfg.device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     dr_train_free(m);
+    dr_comm_free(m);
     void* ptrs[] = {m->d_xtc_tr, m->d_whT, m->d_himg, m->d_dn, m->d_tc_dbg, m->d_wihm, m->d_grad, m->d_adam_m, m->d_adam_v, m->d_dropmask, m->d_blob, m->d_mask, m->d_wf, m->d_bias4, m->d_ct, m->d_abar, m->d_hb, m->d_wtc,
                     m->ws_xT[0], m->ws_xT[1], m->ws_xT[2], m->ws_xT[3], m->ws_xtc[0], m->ws_xtc[1], m->ws_xtc[2], m->ws_xtc[3], m->ws_p[0], m->ws_p[1], m->ws_p[2], m->ws_p[3], m->ws_S[0], m->ws_S[1], m->ws_S[2], m->ws_S[3], m->d_out, m->d_xin, m->d_loss, m->d_y};
     for (void* p : ptrs) if (p) cudaFree(p);

@@ -85,6 +85,8 @@ struct dr_model {
     cudaStream_t own_stream;
     long long x_bstride;            // 0 = dense windows [B,T,F]; else floats between window starts (series mode, N1)
     float* d_dn; bool dn_on; float dn_clamp;   // optional output transform: scale[M_loc] | offset[M_loc] (N2)
+    unsigned int* tile_count; unsigned int* tile_flag; unsigned int tile_value;   // per-tile completion signal of the next K1 launch (dr_comm.cu), or null
+    void* comm;                     // expert-sharded forward state (DrComm, dr_comm.cu)
     int tc_xdrop;                   // precision probe: drop one split term of the x-part (dr_debug_read "tc_xdrop1"/"tc_xdrop2"/"tc_xdrop0")
     unsigned long long* d_tc_dbg;   // optional cycle breakdown of the tcgen05 kernel (dr_debug_read "tc_timing")
     cudaStream_t copy_stream;       // H2D/D2H of the pipelined host entry point
@@ -168,6 +170,13 @@ void dr_train_free(dr_model* m);
 int dr_head_tc_prep(dr_model* m);
 int dr_launch_heads_tc(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 int dr_launch_heads_tc_dst(dr_model* m, const float* S_dev, int B, int T, void* const* dst_ptrs, int n_dst, long long row0);
+// head kernel over a chunk of a larger batch with the cross-expert sum given as `nsrc` partial sums (expert-sharded forward):
+// source w covers the chunk's windows at src[w] + layout [T][64][src_rows[w]][4], first window src_b0[w]; partials are added in
+// source order (rank order: bit-identical on every rank).  P is the full batch's partial workspace (p_tiles 128-window tiles
+// per step), the chunk starts at tile p_tile0.
+int dr_launch_heads_tc_multi(dr_model* m, const float* const* src, const int* src_rows, const int* src_b0, int nsrc,
+                             const float* P, int p_tiles, int p_tile0, int B, int T, float* out_local);
+void dr_comm_free(dr_model* m);
 // dr_head.cu
 int dr_launch_heads(dr_model* m, const float* S_dev, int B, int T, float* out_local_dev);
 int dr_launch_interleave(dr_model* m, const float* gathered, int B, int T, float* out);

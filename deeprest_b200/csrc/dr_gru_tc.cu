@@ -79,6 +79,12 @@ __device__ __forceinline__ void store_bhn(uint32_t taddr, const float* src) {
 //   coalesced 512-byte runs per warp instead of 16 bytes per lane per row.  hs stays row-major (read by the head kernels).
 struct TcTrainOut { float* rzn; float* q; float* hs; long long dir_stride_rows; int lane_major; };
 
+// Completion signal per 256-window tile (expert-sharded forward, csrc/dr_comm.cu): the last work item of a tile to finish
+// writes `value` into flag[tile] with system scope, after every thread has fenced its REDs into S and its stores into P.
+// A stream memory-wait on that word (no SM involved) releases the DMA copies of this tile's partial S to the peers while
+// the kernel — ONE launch for the whole batch — keeps running the next tiles.
+struct TcTileSignal { unsigned int* count; unsigned int* flag; unsigned int value; };
+
 template <bool kTiming, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][kWBytes]
@@ -90,7 +96,8 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                  int B, int T, int Bp, int M_loc, int ntiles,
                  unsigned long long* __restrict__ dbg /* nullable: cycle breakdown of work item 0 */,
                  TcTrainOut tr /* used only when kTrain */,
-                 int xdrop /* 0: all three split terms of the x-part; 1 / 2: drop hi*lo / lo*hi (precision probe only) */) {
+                 int xdrop /* 0: all three split terms of the x-part; 1 / 2: drop hi*lo / lo*hi (precision probe only) */,
+                 TcTileSignal sig /* nullable counters: publish "all work items of this 256-window tile are done" */) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t cta = cluster_ctarank();
@@ -469,9 +476,18 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
         __syncwarp();
     }
 
+    if (sig.count != nullptr) __threadfence();           // this thread's REDs / stores are performed before the item is counted
     tc_fence_before();
     cluster_sync_all();
     if (warp == kMmaWarp) tmem_dealloc<2>(tbase, 512);
+    if (sig.count != nullptr && cta == 0 && tid == 0) {
+        const unsigned int done = atomicAdd(sig.count + tile, 1u) + 1u;
+        if (done == (unsigned int)(2 * M_loc)) {
+            sig.count[tile] = 0;                            // re-armed for the next launch (stream-ordered after this one)
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned int*>(sig.flag + tile) = sig.value;
+        }
+    }
 }
 
 // ---- operand image builders -------------------------------------------------------------------
@@ -600,16 +616,17 @@ int dr_launch_gru_tc(dr_model* m, const float* x, int B, int T, float* S, float*
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     int items = m->M_loc * 2 * ntiles;
+    const TcTileSignal sig{m->tile_count, m->tile_flag, m->tile_value};
     cudaEvent_t* ev = dr_prof_slot(m);
     if (ev) DR_CUDA(m, cudaEventRecord(ev[0], m->stream));
     if (m->d_tc_dbg)
         dr_gru_tc_kernel<true, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg, TcTrainOut{}, m->tc_xdrop);
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, m->d_tc_dbg, TcTrainOut{}, m->tc_xdrop, sig);
     else
         dr_gru_tc_kernel<false, false><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
             reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc), m->d_bias4, m->d_ct,
-            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{}, m->tc_xdrop);
+            S, m->d_p, B, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{}, m->tc_xdrop, sig);
     DR_CUDA(m, cudaGetLastError());
     if (ev) DR_CUDA(m, cudaEventRecord(ev[1], m->stream));
     m->launches += 2;
@@ -636,7 +653,7 @@ int dr_launch_gru_tc_train(dr_model* m, const float* x, int Bm, int T, float* rz
     const int items = m->M_loc * 2 * ntiles;
     dr_gru_tc_kernel<false, true><<<items * 2, kThreads, kSmemBytes, m->stream>>>(
         reinterpret_cast<const uint8_t*>(m->d_wtc), reinterpret_cast<const uint8_t*>(m->d_xtc_tr), m->d_bias4, m->d_ct,
-        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows, lane_major}, 0);
+        nullptr, nullptr, Bm, T, Bp, m->M_loc, ntiles, nullptr, TcTrainOut{rzn, q, hs, dir_stride_rows, lane_major}, 0, TcTileSignal{nullptr, nullptr, 0u});
     DR_CUDA(m, cudaGetLastError());
     m->launches += 2;
     return DR_OK;

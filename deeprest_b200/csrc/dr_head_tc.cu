@@ -45,15 +45,23 @@ struct HeadDst {
     long long row0;     // first window of this call inside the destination (chunked callers)
 };
 
+// The cross-expert sum as up to 8 partial sums (one per rank of an expert-sharded model; one for a single GPU).  Source w
+// holds the chunk's windows in the layout [T][64][rows[w]][4] starting at its window b0[w]; they are added in index order.
+struct HeadSrc {
+    const float* ptr[8];
+    int rows[8], b0[8];
+    int n;
+};
+
 enum HBar { A_READY = 0, A_FREE, B_FULL0, B_FULL1, B_EMPTY0, B_EMPTY1, D_FULL, D_FREE, P_FULL0, P_FULL1, P_EMPTY0, P_EMPTY1, H_NUM };
 
 __global__ void __launch_bounds__(kHThreads, 1)
-dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
+dr_head_tc_kernel(HeadSrc src,                        // partial sums of S, each [T][64][rows][4]
                   const uint8_t* __restrict__ wimg,   // [n_chunks][2 khalf][kBTile]
                   const float* __restrict__ hb,       // [M_loc*Q]
-                  const float* __restrict__ P,        // [T][Bp/128][ceil(N/16)][4][16][128]
+                  const float* __restrict__ P,        // [T][p_tiles][ceil(N/16)][4][16][128]; this call's first tile is p_tile0
                   HeadDst dst,
-                  int B, int T, int Bp, int N, int n_chunks,
+                  int B, int T, int p_tiles, int p_tile0, int N, int n_chunks,
                   const float* __restrict__ dn_scale, const float* __restrict__ dn_offset, float clamp_min) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,9 +99,14 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
                 for (int kg2 = 0; kg2 < 16; ++kg2) {          // two k-groups -> one 16-byte fp16 chunk (8 k)
                     float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
                     if (live) {
-                        const float* sp = S + (((size_t)t * 64 + kh * 32 + kg2 * 2) * Bp + b) * 4;
-                        v0 = *reinterpret_cast<const float4*>(sp);
-                        v1 = *reinterpret_cast<const float4*>(sp + (size_t)Bp * 4);
+                        for (int w = 0; w < src.n; ++w) {          // fixed order: the sum is bit-identical on every rank
+                            const size_t rw = (size_t)src.rows[w];
+                            const float* sp = src.ptr[w] + (((size_t)t * 64 + kh * 32 + kg2 * 2) * rw + src.b0[w] + b) * 4;
+                            const float4 a0 = *reinterpret_cast<const float4*>(sp);
+                            const float4 a1 = *reinterpret_cast<const float4*>(sp + rw * 4);
+                            v0.x += a0.x; v0.y += a0.y; v0.z += a0.z; v0.w += a0.w;
+                            v1.x += a1.x; v1.y += a1.y; v1.z += a1.z; v1.w += a1.w;
+                        }
                     }
                     const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
                     uint32_t hi[4], lo[4];
@@ -206,7 +219,7 @@ dr_head_tc_kernel(const float* __restrict__ S,        // [T][64][Bp][4]
         if (elect_one()) {
             uint32_t n = 0, np = 0;
             const int ngrp16 = (N + 15) >> 4;
-            const uint8_t* pcta = reinterpret_cast<const uint8_t*>(P) + ((size_t)t * (Bp >> 7) + blockIdx.x) * ngrp16 * kPSlab;
+            const uint8_t* pcta = reinterpret_cast<const uint8_t*>(P) + ((size_t)t * p_tiles + p_tile0 + blockIdx.x) * ngrp16 * kPSlab;
             for (int g = 0; g < n_groups; ++g) {
                 const int cg0 = g * kGroupChunks, cg1 = min(n_chunks, cg0 + kGroupChunks);
                 for (int kh = 0; kh < 2; ++kh)
@@ -284,8 +297,10 @@ int dr_launch_heads_tc_dst(dr_model* m, const float* S, int B, int T, void* cons
     int n_chunks = (N + kNC - 1) / kNC;
     DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
     dim3 grid((B + 127) / 128, T);
+    HeadSrc src{};
+    src.ptr[0] = S; src.rows[0] = dr_s_rows(B); src.b0[0] = 0; src.n = 1;
     dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
-        S, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B), N, n_chunks,
+        src, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B) >> 7, 0, N, n_chunks,
         m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
@@ -301,8 +316,32 @@ int dr_launch_heads_tc(dr_model* m, const float* S, int B, int T, float* out_loc
     int n_chunks = (N + kNC - 1) / kNC;
     DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
     dim3 grid((B + 127) / 128, T);
+    HeadSrc src{};
+    src.ptr[0] = S; src.rows[0] = dr_s_rows(B); src.b0[0] = 0; src.n = 1;
     dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
-        S, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B), N, n_chunks,
+        src, m->d_himg, m->d_hb, m->d_p, dst, B, T, dr_s_rows(B) >> 7, 0, N, n_chunks,
+        m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
+    DR_CUDA(m, cudaGetLastError());
+    m->launches += 1;
+    return DR_OK;
+}
+
+int dr_launch_heads_tc_multi(dr_model* m, const float* const* srcp, const int* src_rows, const int* src_b0, int nsrc,
+                             const float* P, int p_tiles, int p_tile0, int B, int T, float* out_local) {
+    int N = m->M_loc * DR_Q;
+    if (N == 0) return DR_OK;
+    if (nsrc < 1 || nsrc > 8) return dr_fail(m, DR_EINVAL, "head kernel: 1..8 partial sums");
+    HeadDst dst;
+    for (int w = 0; w < 8; ++w) dst.ptr[w] = nullptr;
+    dst.ptr[0] = out_local; dst.world = 1; dst.ld = N; dst.col0 = 0; dst.row0 = 0;
+    HeadSrc src{};
+    for (int w = 0; w < nsrc; ++w) { src.ptr[w] = srcp[w]; src.rows[w] = src_rows[w]; src.b0[w] = src_b0[w]; }
+    src.n = nsrc;
+    int n_chunks = (N + kNC - 1) / kNC;
+    DR_CUDA(m, cudaFuncSetAttribute(dr_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHSmem));
+    dim3 grid((B + 127) / 128, T);
+    dr_head_tc_kernel<<<grid, kHThreads, kHSmem, m->stream>>>(
+        src, m->d_himg, m->d_hb, P, dst, B, T, p_tiles, p_tile0, N, n_chunks,
         m->dn_on ? m->d_dn : nullptr, m->dn_on ? m->d_dn + m->M_loc : nullptr, m->dn_clamp);
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;

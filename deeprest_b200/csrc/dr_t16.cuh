@@ -76,7 +76,20 @@ __device__ __forceinline__ uint32_t keep16(const Drop& d, size_t idx) {
     }
     return bits;
 }
-// same for a single element (head-gradient kernel: one thread per column)
+// keep bits of the 4 consecutive elements starting at idx (idx % 4 == 0)
+__device__ __forceinline__ uint32_t keep4(const Drop& d, size_t idx) {
+    if (d.mask) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(d.mask + idx);
+        return ((w & 0xFFu) ? 1u : 0u) | ((w & 0xFF00u) ? 2u : 0u) | ((w & 0xFF0000u) ? 4u : 0u) | ((w & 0xFF000000u) ? 8u : 0u);
+    }
+    if (d.thr16 == 0) return 0xFu;
+    const uint64_t h = mix64(d.seed * 0x9E3779B97F4A7C15ull + (uint64_t)(idx >> 2));
+    uint32_t bits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bits |= (((uint32_t)(h >> (16 * j)) & 0xFFFFu) >= d.thr16 ? 1u : 0u) << j;
+    return bits;
+}
+// same for a single element
 __device__ __forceinline__ bool keep1(const Drop& d, size_t idx) {
     if (d.mask) return d.mask[idx] != 0;
     if (d.thr16 == 0) return true;

@@ -428,36 +428,70 @@ __global__ void dr_adam_kernel(float* __restrict__ w, const float* __restrict__ 
 __global__ void dr_finish_loss_kernel(const double* acc, double inv_n, float* loss) { *loss = (float)(*acc * inv_n); }
 
 // bf16 engine: head weight gradients from the h images.  U[e][q][k] = sum_{t,b} dy r~ ; V = sum dy S ; db = sum dy
-// (dC = U, dA = (V - U)/(M-1); qrnn.py:46-54 differentiated).  grid (M_loc, row chunks), 256 threads = column k of [fwd | rev];
-// rows are walked window-fastest so that a warp's h reads stay inside one 128-byte image row and S lines are reused from L1.
+// (dC = U, dA = (V - U)/(M-1); qrnn.py:46-54 differentiated).  grid (M_loc, row chunks); a thread owns 4 consecutive columns k
+// of [fwd | rev] (one 8-byte h load, one float4 of S in its k-group-major layout, one dropout hash) and every 4th row of the
+// chunk; rows are walked window-fastest, so the 4 row slots of a block read 64 contiguous bytes of S per k-group.
 __global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ S, const float* __restrict__ dy,
                                                               drt16::Drop drop, float* __restrict__ gblob, int off_hw, int off_hb, int pe, float inv_m1,
                                                               int M_loc, int e_lo, int Bfull, int b0, int Bm, int T, int rows_per_chunk) {
-    const int e = blockIdx.x, k = threadIdx.x;
-    const int d = k >> 7, j = k & 127;
+    __shared__ float red[3][2][3][256];               // [slot 1..3][u|v][q][k]
+    const int e = blockIdx.x, kg = threadIdx.x & 63, slot = threadIdx.x >> 6;
+    const int k0 = kg * 4, d = k0 >> 7, j0 = k0 & 127;
     const int ntiles = (Bm + 127) >> 7, Bp = ntiles * 128;
     const size_t rows = (size_t)T * Bm;
     size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
     if (r1 > rows) r1 = rows;
-    float u[3] = {0.f, 0.f, 0.f}, v[3] = {0.f, 0.f, 0.f}, sb[3] = {0.f, 0.f, 0.f};
-    for (size_t r = r0; r < r1; ++r) {
+    float u[3][4], v[3][4], sb[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { u[q][i] = 0.f; v[q][i] = 0.f; }
+    const size_t col_off = (size_t)(j0 >> 6) * drt16::kColBlk + (size_t)(j0 & 7) * 2;
+    const int chunk = (j0 & 63) >> 3;
+#pragma unroll 2
+    for (size_t r = r0 + slot; r < r1; r += 4) {
         const int t = (int)(r / Bm), b = (int)(r % Bm);
-        const uint8_t* hrow = himg + drt16::blk_index(d, e, t, b >> 7, M_loc, T, ntiles) * drt16::kHImg + (size_t)(j >> 6) * drt16::kColBlk +
-                              drt16::img_off(b & 127, (j & 63) >> 3) + (j & 7) * 2;
-        const float h = __uint_as_float((uint32_t)(*reinterpret_cast<const unsigned short*>(hrow)) << 16);
-        const size_t midx = (((size_t)(e_lo + e) * Bfull + b0 + b) * T + t) * DR_2H + k;
-        const float rt = drt16::keep1(drop, midx) ? h * drop.inv_keep : 0.0f;
-        const float s = S[(((size_t)t * 64 + (k >> 2)) * Bp + b) * 4 + (k & 3)];
+        const uint8_t* hrow = himg + drt16::blk_index(d, e, t, b >> 7, M_loc, T, ntiles) * drt16::kHImg + col_off + drt16::img_off(b & 127, chunk);
+        const uint2 hw2 = __ldg(reinterpret_cast<const uint2*>(hrow));
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(S + (((size_t)t * 64 + kg) * Bp + b) * 4));
         const float* dd = dy + (((size_t)b * T + t) * M_loc + e) * DR_Q;
+        const float g0 = __ldg(dd), g1 = __ldg(dd + 1), g2 = __ldg(dd + 2);
+        const uint32_t kb = drt16::keep4(drop, (((size_t)(e_lo + e) * Bfull + b0 + b) * T + t) * DR_2H + k0);
+        const float2 h01 = drt16::unpack_bf2(hw2.x), h23 = drt16::unpack_bf2(hw2.y);
+        const float rt[4] = {(kb & 1u) ? h01.x * drop.inv_keep : 0.f, (kb & 2u) ? h01.y * drop.inv_keep : 0.f,
+                             (kb & 4u) ? h23.x * drop.inv_keep : 0.f, (kb & 8u) ? h23.y * drop.inv_keep : 0.f};
+        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+        const float gq[3] = {g0, g1, g2};
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { const float g = dd[q]; u[q] = fmaf(g, rt, u[q]); v[q] = fmaf(g, s, v[q]); if (k == 0) sb[q] += g; }
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { u[q][i] = fmaf(gq[q], rt[i], u[q][i]); v[q][i] = fmaf(gq[q], sv[i], v[q][i]); }
+            if (kg == 0) sb[q] += gq[q];
+        }
     }
-    float* hw = gblob + (size_t)e * pe + off_hw;      // [Q][4H]: cols 0..2H-1 = A (mean part), 2H.. = C (own part)
+    if (slot > 0) {
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        atomicAdd(hw + (size_t)q * 4 * DR_H + DR_2H + k, u[q]);
-        atomicAdd(hw + (size_t)q * 4 * DR_H + k, (v[q] - u[q]) * inv_m1);
-        if (k == 0) atomicAdd(gblob + (size_t)e * pe + off_hb + q, sb[q]);
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { red[slot - 1][0][q][k0 + i] = u[q][i]; red[slot - 1][1][q][k0 + i] = v[q][i]; }
+    }
+    __shared__ float redb[4][3];
+    if (kg == 0) { redb[slot][0] = sb[0]; redb[slot][1] = sb[1]; redb[slot][2] = sb[2]; }
+    __syncthreads();
+    if (slot == 0) {
+        float* hw = gblob + (size_t)e * pe + off_hw;      // [Q][4H]: cols 0..2H-1 = A (mean part), 2H.. = C (own part)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = k0 + i;
+                const float uu = u[q][i] + red[0][0][q][k] + red[1][0][q][k] + red[2][0][q][k];
+                const float vv = v[q][i] + red[0][1][q][k] + red[1][1][q][k] + red[2][1][q][k];
+                atomicAdd(hw + (size_t)q * 4 * DR_H + DR_2H + k, uu);
+                atomicAdd(hw + (size_t)q * 4 * DR_H + k, (vv - uu) * inv_m1);
+            }
+            if (kg == 0) atomicAdd(gblob + (size_t)e * pe + off_hb + q, redb[0][q] + redb[1][q] + redb[2][q] + redb[3][q]);
+        }
     }
 }
 

@@ -134,18 +134,24 @@ class QuantileRNN:
         return layout.state_dict_from_blob(self.blob(), self.num_metrics, self.input_size)
 
     # ---- forward ---------------------------------------------------------------------
-    def __call__(self, input_seq, out=None):
-        return self.forward(input_seq, out=out)
+    def __call__(self, input_seq, out=None, borrow=False):
+        return self.forward(input_seq, out=out, borrow=borrow)
 
-    def forward(self, input_seq, out=None):
+    def forward(self, input_seq, out=None, borrow=False):
+        """qrnn.py:28-56 in eval mode: [B,T,F] -> [B,T,M,Q].
+
+        Expert-sharded handles (world > 1) take CUDA tensors and return the stacked forecasts on every rank.  The library
+        keeps TWO result tensors per handle and alternates between them, so by default the result is cloned; pass
+        ``borrow=True`` to get a view of the library's tensor instead — it is overwritten by the second-next forward on
+        this handle (a list comprehension ``[model(x, borrow=True) for x in batches]`` would alias)."""
         if self.training and self.dropout_p > 0:
             raise NotImplementedError(
                 "training-mode forward (dropout + autograd, qrnn.py:43 / estimate.py:70-74) is served by "
                 "train_step(); call .eval() for inference")
         if _is_torch(input_seq) and input_seq.is_cuda:
-            return self._forward_torch(input_seq)
+            return self._forward_torch(input_seq, borrow)
         if self.world != 1:
-            raise ValueError("sharded handles take CUDA torch tensors (the collectives run on device buffers)")
+            return self._forward_sharded_host(input_seq, out)
         x = np.ascontiguousarray(input_seq.detach().cpu().numpy() if _is_torch(input_seq) else input_seq,
                                  dtype=np.float32)
         if x.ndim != 3 or x.shape[2] != self.input_size:
@@ -167,7 +173,43 @@ class QuantileRNN:
         _lib.check(self._h, self._lib.dr_set_stream(
             self._h, C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
 
-    def _forward_torch(self, x):
+    # ---- expert-sharded forward through the library's own exchange (csrc/dr_comm.cu) ----
+    def init_comm(self, max_windows, seq_len):
+        """Collective: size this rank's arena for calls up to [max_windows, seq_len] and map the peers' arenas (CUDA IPC
+        handles exchanged through the process group — the only thing torch.distributed does for the forward)."""
+        import torch.distributed as dist
+        handle = (C.c_ubyte * 64)()
+        _lib.check(self._h, self._lib.dr_comm_init(self._h, int(max_windows), int(seq_len), handle, None))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self._pg)
+        buf = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(handles))
+        _lib.check(self._h, self._lib.dr_comm_attach(self._h, buf, None))
+        self._comm_shape = (int(max_windows), int(seq_len))
+
+    def _ensure_comm(self, B, T):
+        shp = getattr(self, "_comm_shape", None)
+        if shp is None or B > shp[0] or T != shp[1]:
+            self.init_comm(B, T)
+
+    def _forward_sharded_host(self, input_seq, out):
+        """numpy / CPU tensors on a sharded handle: H2D of x, the exchange, and the D2H of THIS rank's forecast columns into
+        ``out`` — the full [B,T,M,Q] host array (ranks of one host may share it, e.g. a shared-memory mapping) — all inside
+        ``dr_forward_sharded``."""
+        x = np.ascontiguousarray(input_seq.detach().cpu().numpy() if _is_torch(input_seq) else input_seq, dtype=np.float32)
+        if x.ndim != 3 or x.shape[2] != self.input_size:
+            raise ValueError(f"input_seq must be [B,T,{self.input_size}], got {x.shape}")
+        B, T, _ = x.shape
+        if out is None:
+            out = np.zeros((B, T, self.num_metrics, layout.Q), np.float32)
+        elif out.shape != (B, T, self.num_metrics, layout.Q) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 [B,T,M,Q] array")
+        self._ensure_comm(B, T)
+        self._lib.dr_set_stream(self._h, None, 0)
+        fp = C.POINTER(C.c_float)
+        _lib.check(self._h, self._lib.dr_forward_sharded(self._h, x.ctypes.data_as(fp), B, T, out.ctypes.data_as(fp), None))
+        return out
+
+    def _forward_torch(self, x, borrow=False):
         import torch
         if x.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.input_size:
             raise ValueError(f"input_seq must be float32 [B,T,{self.input_size}]")
@@ -205,24 +247,39 @@ class QuantileRNN:
         peer = None
         mode = self.gather_mode
         if mode == "auto":
-            mode = "kernel" if self.world <= 2 else "copy"
+            mode = "dma" if (self.input_size <= 64 and self._engine != "ffma") else "copy"
+        if mode == "dma":
+            # the library's own exchange: ONE recurrence launch, partial sums of S moved by the copy engines and added by
+            # the head kernel, forecasts scattered into every rank's tensor by 2-D peer copies (no NCCL, no SM-resident
+            # collective)
+            self._ensure_comm(B, T)
+            ptr = C.c_void_p()
+            _lib.check(h, lib.dr_forward_sharded_dev(h, x.data_ptr(), B, T, C.byref(ptr)))
+
+            class _Buf:
+                def __init__(self, p, shape):
+                    self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (p, False), "version": 2}
+            res = torch.as_tensor(_Buf(ptr.value, (B, T, self.num_metrics, layout.Q)), device=x.device)
+            return res if borrow else res.clone()
         if mode == "kernel" and (self.input_size > 64 or self._engine == "ffma"):
             mode = "copy"                    # peer stores from K2 need the tcgen05 head kernel
         if mode == "copy":
             from .sharding import PeerBuffers
             if self._peer is None:
                 self._peer = PeerBuffers(self._pg)
-            return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
-                                   s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
-                                   interleave_fn=interleave_fn, group=self._pg, peer=self._peer, scatter_fn=scatter_fn)
+            res = sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
+                                  s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
+                                  interleave_fn=interleave_fn, group=self._pg, peer=self._peer, scatter_fn=scatter_fn)
+            return res if borrow else res.clone()          # the symmetric-memory tensors alternate
         if mode == "kernel":
             from .sharding import PeerBuffers
             if self._peer is None:
                 self._peer = PeerBuffers(self._pg)
             peer = self._peer
-        return sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
-                               s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
-                               interleave_fn=interleave_fn, group=self._pg, peer=peer, heads_p2p_fn=heads_p2p_fn)
+        res = sharded_forward(x, world=self.world, m_local=self.m_local, q=layout.Q,
+                              s_elems=lambda bn: lib.dr_s_elems(bn, T), local_fn=local_fn, heads_fn=heads_fn,
+                              interleave_fn=interleave_fn, group=self._pg, peer=peer, heads_p2p_fn=heads_p2p_fn)
+        return res if (borrow or peer is None) else res.clone()
 
     # ---- steps either side of the path ----------------------------------------
     def forward_series(self, series, window_size, stride=1):
@@ -261,6 +318,8 @@ class QuantileRNN:
         (dropout on the GRU outputs), ``quantile_loss``, backward, ``Adam(lr)`` step.  Returns the
         loss (float).  ``dropout_mask`` ([M,B,T,2H] of 0/1) replays a mask for parity tests;
         otherwise a counter-based RNG keyed by ``seed`` draws it on the device."""
+        if _is_torch(inputs) and inputs.is_cuda:
+            return self._train_step_torch(inputs, labels, lr, dropout_mask, seed)
         x = np.ascontiguousarray(inputs.detach().cpu().numpy() if _is_torch(inputs) else inputs, np.float32)
         y = np.ascontiguousarray(labels.detach().cpu().numpy() if _is_torch(labels) else labels, np.float32)
         if x.ndim != 3 or x.shape[2] != self.input_size or y.shape != (x.shape[0], x.shape[1], self.num_metrics):
@@ -277,6 +336,31 @@ class QuantileRNN:
         _lib.check(self._h, self._lib.dr_train_step(self._h, x.ctypes.data_as(fp), y.ctypes.data_as(fp), B, T, mptr,
                                                     C.c_uint64(int(seed)), C.c_float(lr), C.byref(loss)))
         return float(loss.value)
+
+    def _train_step_torch(self, inputs, labels, lr, dropout_mask, seed):
+        """Device-resident variant (CUDA torch tensors, ``dr_train_step_dev`` on torch's current stream): nothing is copied;
+        returns the loss as a 0-dim CUDA tensor.  The train-mode forecasts of the step are kept in ``self.train_outputs``."""
+        import torch
+        if self.world != 1:
+            raise ValueError("sharded handles use train_step_sharded")
+        x = inputs.contiguous()
+        y = labels.contiguous()
+        if x.dtype != torch.float32 or y.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.input_size \
+                or tuple(y.shape) != (x.shape[0], x.shape[1], self.num_metrics):
+            raise ValueError("inputs must be float32 [B,T,F] and labels float32 [B,T,M]")
+        B, T, _ = x.shape
+        mask = None
+        if dropout_mask is not None:
+            mask = torch.as_tensor(np.ascontiguousarray(dropout_mask, np.uint8)).to(x.device)
+        out = getattr(self, "train_outputs", None)
+        if out is None or tuple(out.shape) != (B, T, self.num_metrics, layout.Q) or out.device != x.device:
+            out = self.train_outputs = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        self._bind_stream()
+        _lib.check(self._h, self._lib.dr_train_step_dev(self._h, x.data_ptr(), y.data_ptr(), B, T,
+                                                        mask.data_ptr() if mask is not None else None,
+                                                        C.c_uint64(int(seed)), C.c_float(lr), loss.data_ptr(), out.data_ptr()))
+        return loss
 
     def train_step_sharded(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0):
         """Expert-sharded training step (world > 1).  ``inputs`` [B,T,F] and ``labels`` [B,T,M] are the full tensors

@@ -142,6 +142,29 @@ int  dr_scatter_forecasts_dev(dr_model* m, const float* out_local_dev, int32_t B
 int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int32_t T,
                           float* out_dev);
 
+/* ---- expert-sharded forward as ONE call per rank (no NCCL, no host-side collectives; csrc/dr_comm.cu) ----
+ * The cross-expert mean (qrnn.py:46-52) needs the sum S over ALL experts.  Every rank owns an "arena" of device memory that
+ * its peers map; the recurrence kernel runs as one launch and flags finished 256-window tiles, copy engines move each tile's
+ * partial S to the peers, the head kernel adds the partials in rank order (bit-identical on every rank) and the forecast
+ * columns are placed into every rank's stacked tensor [B,T,M,Q] (qrnn.py:55) by strided 2-D peer copies.
+ *   dr_comm_init   : allocate this rank's arena for calls up to [Bmax, T]; returns its CUDA IPC handle (64 bytes; for one
+ *                    process per GPU) and its device pointer (for several handles inside one process).  Collective in the
+ *                    sense that every rank must have returned from it before any rank calls dr_comm_attach.
+ *   dr_comm_attach : map the peers' arenas — `ipc_handles` = world x 64 bytes in rank order (own entry ignored), or
+ *                    `arena_ptrs` = world device pointers of the same process (peer access is enabled here).
+ *   dr_forward_sharded_dev : x_dev [B,T,F] (replicated) -> *out_dev = the stacked forecasts [B,T,M,Q] in this rank's arena.
+ *                    Asynchronous on the handle's stream (dr_set_stream).  The tensor stays valid until the second-next
+ *                    sharded forward on this handle (two tensors alternate); copy it if it must live longer.
+ *   dr_forward_sharded     : host entry point.  x_host [B,T,F]; this rank's forecast columns are written to
+ *                    out_host[b, t, rank*M/world ..., :] where out_host is the FULL [B,T,M,Q] tensor (row pitch M*Q floats;
+ *                    ranks of one host may share it), chunk by chunk while later chunks still compute; returns when they are
+ *                    there.  *out_dev (nullable) as above.  tcgen05 engine (input_size <= 64) only. */
+int64_t dr_comm_arena_bytes(const dr_model* m, int32_t Bmax, int32_t T);
+int  dr_comm_init  (dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out /* 64 bytes, nullable */, void** arena_ptr_out /* nullable */);
+int  dr_comm_attach(dr_model* m, const void* ipc_handles /* nullable */, void* const* arena_ptrs /* nullable */);
+int  dr_forward_sharded_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T, float** out_dev);
+int  dr_forward_sharded    (dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host, float** out_dev);
+
 /* ---- loss: replaces QuantileRNN.quantile_loss (qrnn.py:58-67) ----
  * out [B,T,M,Q], y [B,T,M] -> scalar pinball loss (mean over M of mean over B,T of sum over Q) */
 int  dr_quantile_loss    (dr_model* m, const float* out_host, const float* y_host,
