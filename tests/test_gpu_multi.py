@@ -40,7 +40,8 @@ def _worker(rank, world, port, path, engine, fused):
         others = [model(x * 0.5) for _ in range(3)]
         torch.cuda.synchronize()
         assert torch.equal(out, keep), "a returned forecast tensor was overwritten by later forwards"
-        assert all(torch.equal(o, others[0]) for o in others[1:])
+        # (bit-identity ACROSS calls is not expected: the fp32 REDs into S commute in a different order every launch)
+        assert all(float((o - others[0]).abs().max()) < 1e-6 for o in others[1:])
         assert torch.equal(out, out2) or float((out - out2).abs().max()) < 1e-6
         np.save(f"{path}.{rank}.npy", out.cpu().numpy())
         if fused == "dma":
