@@ -58,6 +58,8 @@ SIGNATURES = {
     "dr_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dr_comm_attach": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dr_forward_sharded_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "dr_forward_sharded_issue_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+    "dr_forward_sharded_wait": (C.c_int, [_H, C.c_int32]),
     "dr_forward_sharded": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dr_quantile_loss": (C.c_int, [_H, _FP, _FP, C.c_int32, C.c_int32, _FP]),
     "dr_quantile_loss_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

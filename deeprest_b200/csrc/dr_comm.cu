@@ -33,7 +33,7 @@ struct DrComm {
     size_t off_S, s_slot, off_out, out_set;
     unsigned int epoch;
     cudaStream_t cs, ss, xs, os, ds;               // recurrence | S sends | head kernels | forecast scatter | D2H (host entry)
-    cudaEvent_t ev_call, ev_done, ev_k2[kMaxChunks], ev_x, ev_xs_end[2], ev_ss_end[2], ev_os_end[2], ev_d2h;
+    cudaEvent_t ev_call, ev_done[2], ev_k2[kMaxChunks], ev_x, ev_xs_end[2], ev_ss_end[2], ev_os_end[2], ev_d2h;
     unsigned int *tile_count, *tile_flag;          // local, written by the recurrence kernel
     unsigned int* d_ring; unsigned int* h_ring;    // epoch values staged for the 4-byte signal copies
     float* S_full[2]; size_t S_cap[2];
@@ -79,7 +79,7 @@ void dr_comm_free(dr_model* m) {
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_ring) cudaFreeHost(c->h_ring);
     for (cudaStream_t s : sts) if (s) cudaStreamDestroy(s);
-    cudaEvent_t evs[] = {c->ev_call, c->ev_done, c->ev_x, c->ev_xs_end[0], c->ev_xs_end[1], c->ev_ss_end[0], c->ev_ss_end[1],
+    cudaEvent_t evs[] = {c->ev_call, c->ev_done[0], c->ev_done[1], c->ev_x, c->ev_xs_end[0], c->ev_xs_end[1], c->ev_ss_end[0], c->ev_ss_end[1],
                          c->ev_os_end[0], c->ev_os_end[1], c->ev_d2h};
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int i = 0; i < kMaxChunks; ++i) if (c->ev_k2[i]) cudaEventDestroy(c->ev_k2[i]);
@@ -133,7 +133,7 @@ int dr_comm_init(dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out, voi
     DR_CUDA(m, cudaStreamCreateWithPriority(&c->xs, cudaStreamNonBlocking, hi));   // head kernels get freed SMs before queued recurrence CTAs
     DR_CUDA(m, cudaStreamCreateWithPriority(&c->os, cudaStreamNonBlocking, hi));
     DR_CUDA(m, cudaStreamCreateWithPriority(&c->ds, cudaStreamNonBlocking, hi));
-    cudaEvent_t* evs[] = {&c->ev_call, &c->ev_done, &c->ev_x, &c->ev_xs_end[0], &c->ev_xs_end[1], &c->ev_ss_end[0], &c->ev_ss_end[1],
+    cudaEvent_t* evs[] = {&c->ev_call, &c->ev_done[0], &c->ev_done[1], &c->ev_x, &c->ev_xs_end[0], &c->ev_xs_end[1], &c->ev_ss_end[0], &c->ev_ss_end[1],
                           &c->ev_os_end[0], &c->ev_os_end[1], &c->ev_d2h};
     for (cudaEvent_t* e : evs) DR_CUDA(m, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < kMaxChunks; ++i) DR_CUDA(m, cudaEventCreateWithFlags(&c->ev_k2[i], cudaEventDisableTiming));
@@ -188,7 +188,7 @@ int reserve_f(dr_model* m, float** p, size_t* cap, size_t bytes) { return dr_res
 
 // The whole sharded forward, enqueued asynchronously.  x is on the device.  If out_host is given, this rank's own forecast
 // columns are additionally copied to out_host[b,t,rank*M_loc..,:] (row pitch = M*Q floats) chunk by chunk.
-int forward_sharded(dr_model* m, const float* x, int B, int T, float** out_dev, float* out_host) {
+int forward_sharded(dr_model* m, const float* x, int B, int T, float** out_dev, float* out_host, bool wait_caller, int32_t* ticket) {
     DrComm* c = comm_of(m);
     if (!c || !c->attached) return dr_fail(m, DR_ESTATE, "sharded forward before dr_comm_init / dr_comm_attach");
     if (B > c->Bmax || T != c->T) return dr_fail(m, DR_EINVAL, "sharded forward: shape exceeds what dr_comm_init sized the arena for");
@@ -316,8 +316,9 @@ int forward_sharded(dr_model* m, const float* x, int B, int T, float** out_dev, 
             if ((rc = wait_flag(m, c, c->os, c->arena + flag_odone(p, ch), n))) return rc;
         }
     DR_CUDA(m, cudaEventRecord(c->ev_os_end[set], c->os));
-    DR_CUDA(m, cudaEventRecord(c->ev_done, c->os));
-    DR_CUDA(m, cudaStreamWaitEvent(caller, c->ev_done, 0));
+    DR_CUDA(m, cudaEventRecord(c->ev_done[set], c->os));
+    if (wait_caller) DR_CUDA(m, cudaStreamWaitEvent(caller, c->ev_done[set], 0));
+    if (ticket) *ticket = (int32_t)n;
     if (out_host) {
         DR_CUDA(m, cudaEventRecord(c->ev_d2h, c->ds));
         DR_CUDA(m, cudaStreamWaitEvent(caller, c->ev_d2h, 0));
@@ -334,7 +335,25 @@ int dr_forward_sharded_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T
     if (!m) return DR_EINVAL;
     if (!x_dev || !out_dev || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "dr_forward_sharded_dev: bad argument");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
-    return forward_sharded(m, x_dev, B, T, out_dev, nullptr);
+    return forward_sharded(m, x_dev, B, T, out_dev, nullptr, true, nullptr);
+}
+
+int dr_forward_sharded_issue_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T, float** out_dev, int32_t* ticket) {
+    if (!m) return DR_EINVAL;
+    if (!x_dev || !out_dev || !ticket || B < 1 || T < 1) return dr_fail(m, DR_EINVAL, "dr_forward_sharded_issue_dev: bad argument");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    return forward_sharded(m, x_dev, B, T, out_dev, nullptr, false, ticket);
+}
+
+int dr_forward_sharded_wait(dr_model* m, int32_t ticket) {
+    if (!m) return DR_EINVAL;
+    DrComm* c = comm_of(m);
+    if (!c || !c->attached) return dr_fail(m, DR_ESTATE, "dr_forward_sharded_wait before dr_comm_init / dr_comm_attach");
+    const unsigned int n = (unsigned int)ticket;
+    if (n == 0 || n > c->epoch || c->epoch - n > 1) return dr_fail(m, DR_EINVAL, "dr_forward_sharded_wait: the ticket must be one of the last two forwards");
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    DR_CUDA(m, cudaStreamWaitEvent(m->stream, c->ev_done[n & 1u], 0));
+    return DR_OK;
 }
 
 int dr_forward_sharded(dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host, float** out_dev) {
@@ -348,7 +367,7 @@ int dr_forward_sharded(dr_model* m, const float* x_host, int32_t B, int32_t T, f
     if (rc) return rc;
     DR_CUDA(m, cudaMemcpyAsync(c->x_stage, x_host, nx, cudaMemcpyHostToDevice, m->stream));
     float* dev = nullptr;
-    rc = forward_sharded(m, c->x_stage, B, T, &dev, out_host);
+    rc = forward_sharded(m, c->x_stage, B, T, &dev, out_host, true, nullptr);
     if (rc) return rc;
     DR_CUDA(m, cudaStreamSynchronize(m->stream));                   // own columns are in out_host, the stacked tensor is complete on the device
     if (out_dev) *out_dev = dev;

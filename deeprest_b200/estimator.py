@@ -209,6 +209,32 @@ class QuantileRNN:
         _lib.check(self._h, self._lib.dr_forward_sharded(self._h, x.ctypes.data_as(fp), B, T, out.ctypes.data_as(fp), None))
         return out
 
+    def forward_async(self, x):
+        """Expert-sharded handles: issue a forward without making torch's current stream wait for it; returns an object
+        whose ``wait()`` orders the current stream after the result and returns the (borrowed) forecast tensor.  With the
+        next batch issued before the previous result is consumed, the exchange tail of one forward runs under the
+        recurrence of the next (two forwards in flight; the library alternates two result tensors)."""
+        import torch
+        if self.world == 1:
+            raise ValueError("forward_async is for expert-sharded handles")
+        x = x.contiguous()
+        B, T, _ = x.shape
+        self._bind_stream()
+        self._ensure_comm(B, T)
+        ptr, ticket = C.c_void_p(), C.c_int32()
+        _lib.check(self._h, self._lib.dr_forward_sharded_issue_dev(self._h, x.data_ptr(), B, T, C.byref(ptr), C.byref(ticket)))
+        owner, shape, dev = self, (B, T, self.num_metrics, layout.Q), x.device
+
+        class _Pending:
+            def wait(self_inner):
+                owner._bind_stream()
+                _lib.check(owner._h, owner._lib.dr_forward_sharded_wait(owner._h, ticket.value))
+
+                class _Buf:
+                    __cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+                return torch.as_tensor(_Buf(), device=dev)
+        return _Pending()
+
     def _forward_torch(self, x, borrow=False):
         import torch
         if x.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.input_size:

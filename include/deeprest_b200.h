@@ -164,6 +164,14 @@ int  dr_comm_init  (dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out /
 int  dr_comm_attach(dr_model* m, const void* ipc_handles /* nullable */, void* const* arena_ptrs /* nullable */);
 int  dr_forward_sharded_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T, float** out_dev);
 int  dr_forward_sharded    (dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host, float** out_dev);
+/*   Two forwards in flight: dr_forward_sharded_dev makes the handle's stream wait for its result before it returns control of
+ *   that stream, so the next forward's recurrence starts only after this forward's exchange tail.  A serving loop that has
+ *   the next batch ready issues it first and consumes the previous result afterwards:
+ *     dr_forward_sharded_issue_dev(batch n+1) -> *ticket;   dr_forward_sharded_wait(ticket of batch n);   use result n
+ *   _issue_dev enqueues everything but does not touch the handle's stream after reading x; _wait makes the handle's stream
+ *   wait for that forward (one of the last two). */
+int  dr_forward_sharded_issue_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T, float** out_dev, int32_t* ticket);
+int  dr_forward_sharded_wait     (dr_model* m, int32_t ticket);
 
 /* ---- loss: replaces QuantileRNN.quantile_loss (qrnn.py:58-67) ----
  * out [B,T,M,Q], y [B,T,M] -> scalar pinball loss (mean over M of mean over B,T of sum over Q) */

@@ -43,6 +43,13 @@ def _worker(rank, world, port, path, engine, fused):
         # (bit-identity ACROSS calls is not expected: the fp32 REDs into S commute in a different order every launch)
         assert all(float((o - others[0]).abs().max()) < 1e-6 for o in others[1:])
         assert torch.equal(out, out2) or float((out - out2).abs().max()) < 1e-6
+        if fused == "dma":                   # two forwards in flight: issue both, then consume them in order
+            p1 = model.forward_async(x)
+            p2 = model.forward_async(x * 0.5)
+            o1 = p1.wait().clone()
+            o2 = p2.wait().clone()
+            torch.cuda.synchronize()
+            assert float((o1 - out).abs().max()) < 1e-6 and float((o2 - others[0]).abs().max()) < 1e-6
         np.save(f"{path}.{rank}.npy", out.cpu().numpy())
         if fused == "dma":
             used = bool(getattr(model, "_comm_shape", None))
