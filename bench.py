@@ -58,6 +58,12 @@ def parse():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the BASELINE configs[2] training block (N=1)")
     ap.add_argument("--no-configs3", action="store_true", help="skip the BASELINE configs[3] block (N=8)")
+    ap.add_argument("--no-configs4", action="store_true", help="skip the BASELINE configs[4] sharded-training block (N=8)")
+    ap.add_argument("--configs4", action="store_true", help="run the configs[4] block at this world size too (testing)")
+    ap.add_argument("--train4-services", type=int, default=512)
+    ap.add_argument("--train4-batch", type=int, default=1024)
+    ap.add_argument("--train4-seq-len", type=int, default=1440)
+    ap.add_argument("--train4-steps", type=int, default=2)
     ap.add_argument("--train-services", type=int, default=256)
     ap.add_argument("--train-batch", type=int, default=4096)
     ap.add_argument("--train-steps", type=int, default=3)
@@ -377,6 +383,50 @@ def train_block(args, dev, peaks):
     return blk
 
 
+# --------------------------------------------------------------------------- sharded training block (N = 8)
+def train_sharded_block(args, rank, world, dev, peaks):
+    """BASELINE configs[4]: long-horizon training, seq_len 1440, 512 services (1024 experts) sharded over the GPUs by
+    service ID, bf16.  Experts, Adam moments and gradients are expert-local (no gradient all-reduce exists); the three
+    cross-rank sums of a step (S, G-bar per micro-batch, the loss scalar) run through NCCL between the library's phases."""
+    import torch
+    import torch.distributed as dist
+    from deeprest_b200 import QuantileRNN, synth
+    S, B, T, F = args.train4_services, args.train4_batch, args.train4_seq_len, args.features
+    M = 2 * S
+    M_loc = M // world
+    lo, hi = rank * M_loc, (rank + 1) * M_loc
+    m = QuantileRNN(F, M, dtype="bf16", device=dev.index, process_group=dist.group.WORLD, rank=rank, world=world)
+    m.load_blob(synth.weights(WSEED, M, F, experts=(lo, hi)))
+    x = torch.from_numpy(synth.windows(XSEED, B, T, F)).to(dev)
+    y = ((torch.arange(T, device=dev, dtype=torch.float32)[None, :, None] % 17) / 17.0).expand(B, T, M_loc).contiguous()
+    loss = m.train_step_sharded(x, y, seed=1, local_labels=True)
+    dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.train4_steps):
+        loss = m.train_step_sharded(x, y, seed=2 + i, local_labels=True)
+    e1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.train4_steps
+    flops = 3.0 * algorithmic_flops(M, B, T, F)
+    named = (S == 512 and T == 1440 and world == 8)
+    blk = {"workload": ("BASELINE configs[4]" if named else "BASELINE configs[4]-shaped") +
+                       f": long-horizon training step, {S} services ({M} experts) sharded x{world} ({M_loc} experts per GPU), batch {B}, seq_len {T}, F={F}, bf16",
+           "dtype": "bf16", "data": "synthetic", "ms_per_step": ms, "value": S * B / (ms * 1e-3), "unit": UNIT, "steps": args.train4_steps,
+           "warmup": 1, "loss": float(loss), "engine": m.last_engine, "parallelism": f"expert-shard x{world}",
+           "roofline": {"bound": "tensor", "algorithmic_flops_per_step": flops, "achieved": flops / (ms * 1e-3) / 1e12,
+                        "peak": peaks["tensor_tflops"] * world, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / (peaks["tensor_tflops"] * world)},
+           "collectives": "all-reduce of S and of the head adjoint G-bar per micro-batch, and of the loss scalar (NCCL, torch.distributed); no gradient all-reduce",
+           "parity": "tests/test_gpu_train.py::test_bf16_long_horizon_training_parity (T=1440) and tests/test_gpu_multi.py::test_two_gpu_sharded_bf16_train_step_matches_oracle"}
+    m.close()
+    del x, y
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return blk
+
+
 # --------------------------------------------------------------------------- our arm
 def shared_host_tensor(shape, rank, world, tag):
     """One pinned host tensor shared by the ranks of this box (POSIX shared memory): every rank's D2H lands in its own
@@ -580,6 +630,17 @@ def run_ours(args, rank, world, local_rank):
     B, T, F = args.windows, args.seq_len, args.features
     peaks = measured_peaks()
 
+    blk4 = None
+    # (runs FIRST: its tens-of-GB activation images must be allocated before this process maps any peer memory through CUDA
+    #  IPC — afterwards cudaMalloc of that size fails with "resource already mapped" on this driver)
+    # ---- BASELINE configs[4]: long-horizon bf16 training, experts sharded over the GPUs ----
+    if world > 1 and (world == 8 or args.configs4) and not args.no_configs4:
+        try:
+            blk4 = train_sharded_block(args, rank, world, dev, peaks)
+        except Exception as exc:
+            import traceback
+            log("configs4 block failed:\n" + traceback.format_exc())
+            blk4 = {"unavailable": repr(exc)}
     res, final, e2e_final, x_host = measure_inference(args, rank, world, dev, S, B, T, F, peaks, "main")
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": N, "steps": args.steps,
@@ -589,6 +650,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": res["roofline"], "batch_windows_per_sec": res["batch_windows_per_sec"],
         "batches_in_flight": res["batches_in_flight"],
     }
+    if blk4 is not None:
+        line["configs4"] = blk4
     if rank == 0:
         M = 2 * S
         cs = None
@@ -623,6 +686,8 @@ def run_ours(args, rank, world, local_rank):
         try:
             line["train"] = train_block(args, dev, peaks)
         except Exception as exc:
+            import traceback
+            log("train block failed:\n" + traceback.format_exc())
             line["train"] = {"unavailable": repr(exc)}
     if rank == 0:
         print(json.dumps(line), flush=True)

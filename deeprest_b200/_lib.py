@@ -57,6 +57,7 @@ SIGNATURES = {
     "dr_comm_arena_bytes": (C.c_int64, [_H, C.c_int32, C.c_int32]),
     "dr_comm_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
     "dr_comm_attach": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dr_comm_detach": (C.c_int, [_H]),
     "dr_forward_sharded_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "dr_forward_sharded_issue_dev": (C.c_int, [_H, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
     "dr_forward_sharded_wait": (C.c_int, [_H, C.c_int32]),
@@ -69,6 +70,7 @@ SIGNATURES = {
     "dr_train_begin_dev": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64,
                                      C.c_float, C.c_void_p, C.c_void_p]),
     "dr_train_advance": (C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "dr_train_set_microbatch": (C.c_int, [_H, C.c_int32]),
     "dr_get_grads": (C.c_int, [_H, _FP, C.c_size_t]),
     "dr_debug_read": (C.c_int, [_H, C.c_char_p, _FP, C.c_size_t]),
     "dr_tc_probe": (C.c_int, [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,

@@ -80,7 +80,7 @@ int dr_create(const dr_config* cfg, dr_model** out) {
     m->d_blob = m->d_mask = m->d_wf = m->d_bias4 = m->d_ct = m->d_abar = m->d_hb = nullptr;
     m->d_wtc = nullptr; m->wtc_bytes = 0;
     m->d_wihm = nullptr; m->d_grad = nullptr; m->d_adam_m = nullptr; m->d_adam_v = nullptr; m->adam_step = 0;
-    m->train_ws = nullptr; m->d_dropmask = nullptr; m->dropmask_cap = 0;
+    m->train_ws = nullptr; m->train_mb = 0; m->d_dropmask = nullptr; m->dropmask_cap = 0;
     m->copy_stream = nullptr; m->stream2 = nullptr; m->d_tc_dbg = nullptr; m->tc_xdrop = 0;
     m->tile_count = nullptr; m->tile_flag = nullptr; m->tile_value = 0; m->comm = nullptr;
     for (int i = 0; i < 4; ++i) { m->ws_S[i] = nullptr; m->ws_S_cap[i] = 0; }

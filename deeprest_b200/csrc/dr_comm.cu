@@ -68,12 +68,20 @@ void layout_arena(DrComm* c, int M_total) {
 
 }  // namespace
 
+// unmap the peers' arenas (after this rank's queued work has drained)
+static void comm_detach(DrComm* c) {
+    cudaStream_t sts[] = {c->cs, c->ss, c->xs, c->os, c->ds};
+    for (cudaStream_t s : sts) if (s) cudaStreamSynchronize(s);
+    for (int p = 0; p < c->world; ++p)
+        if (c->ipc_open[p] && c->peer[p]) { cudaIpcCloseMemHandle(c->peer[p]); c->ipc_open[p] = false; c->peer[p] = nullptr; }
+    c->attached = false;
+}
+
 void dr_comm_free(dr_model* m) {
     DrComm* c = comm_of(m);
     if (!c) return;
     cudaStream_t sts[] = {c->cs, c->ss, c->xs, c->os, c->ds};
-    for (cudaStream_t s : sts) if (s) cudaStreamSynchronize(s);
-    for (int p = 0; p < c->world; ++p) if (c->ipc_open[p] && c->peer[p]) cudaIpcCloseMemHandle(c->peer[p]);
+    comm_detach(c);
     void* ptrs[] = {c->arena, c->tile_count, c->tile_flag, c->d_ring, c->S_full[0], c->S_full[1], c->P_full[0], c->P_full[1],
                     c->out_local[0], c->out_local[1], c->x_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -145,6 +153,15 @@ int dr_comm_init(dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out, voi
         memcpy(ipc_handle_out, &h, sizeof(h));
     }
     if (arena_ptr_out) *arena_ptr_out = c->arena;
+    return DR_OK;
+}
+
+int dr_comm_detach(dr_model* m) {
+    if (!m) return DR_EINVAL;
+    DrComm* c = comm_of(m);
+    if (!c) return DR_OK;
+    DR_CUDA(m, cudaSetDevice(m->cfg.device));
+    comm_detach(c);
     return DR_OK;
 }
 

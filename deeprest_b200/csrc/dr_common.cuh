@@ -57,6 +57,7 @@ struct dr_model {
     float* d_grad;                  // gradients of the last train step, reference blob order [M_loc*per_expert]
     float* d_adam_m; float* d_adam_v; int64_t adam_step;
     void*  train_ws;                // training workspace (dr_train.cu)
+    int    train_mb;                // micro-batch override in windows (dr_train_set_microbatch), 0 = sized from free memory
     void*  d_dropmask; size_t dropmask_cap;
     __nv_bfloat16* d_wtc;           // tcgen05 weight image (hi/lo bf16)      see dr_gru_tc.cu
     size_t wtc_bytes;

@@ -566,31 +566,42 @@ static int train16_begin(dr_model* m, dr_train_ws* ws, int B, int T) {
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             size_t held = (size_t)ws->cap16_tiles * per_tile;
-            budget = std::max<size_t>((size_t)4 << 30, (free_b + held) * 7 / 10);
+            budget = std::max<size_t>((size_t)4 << 30, (free_b + held) * 6 / 10);
         }
     }
     int mb_tiles = (int)std::min<size_t>((size_t)tiles_all, std::max<size_t>(1, budget / std::max<size_t>(per_tile, 1)));
     if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) mb_tiles = std::min(tiles_all, (v + 127) / 128); }   // test hook
-    const int Bm = std::min(B, mb_tiles * 128);
-    if (ws->cap16_tiles < mb_tiles || ws->cap16_T != T) {
-        ws->cap16_tiles = 0; ws->cap16_T = 0;
-        const size_t nt = (size_t)mb_tiles;
-        int rc;
-        if ((rc = ws16_alloc(m, (void**)&ws->w16, dr_t16_wimg_bytes(Ml))) || (rc = ws16_alloc(m, (void**)&ws->whT16, dr_t16_whT_bytes(Ml))) ||
-            (rc = ws16_alloc(m, (void**)&ws->x16, (size_t)T * nt * drt16::kColBlk)) ||
-            (rc = ws16_alloc(m, (void**)&ws->gate16, (size_t)2 * Ml * T * nt * drt16::kGateImg)) ||
-            (rc = ws16_alloc(m, (void**)&ws->h16, (size_t)2 * Ml * T * nt * drt16::kHImg)) ||
-            (rc = ws16_alloc(m, (void**)&ws->zero16, drt16::kColBlk)) ||
-            (rc = ws16_alloc(m, (void**)&ws->S16, (size_t)T * DR_2H * nt * 128 * sizeof(float))) ||
-            (rc = ws16_alloc(m, (void**)&ws->P16, (size_t)T * nt * ngrp * 4 * 16 * 128 * sizeof(float))) ||
-            (rc = ws16_alloc(m, (void**)&ws->dy16, (size_t)nt * 128 * T * Ml * DR_Q * sizeof(float))) ||
-            (rc = ws16_alloc(m, (void**)&ws->gbar16, (size_t)nt * 128 * T * DR_2H * sizeof(float))) ||
-            (rc = ws16_alloc(m, (void**)&ws->Px16, (size_t)2 * Ml * 3 * DR_H * F * sizeof(float))) ||
-            (rc = ws_alloc(m, &ws->dmask, (size_t)Ml * F)))
-            return rc;
+    if (m->train_mb >= 1) mb_tiles = std::min(tiles_all, (m->train_mb + 127) / 128);
+    if (ws->cap16_tiles >= mb_tiles && ws->cap16_T == T) mb_tiles = std::min(tiles_all, ws->cap16_tiles);   // keep what is already there
+    else {
+        // allocate; if the device refuses (memory, or address space when peers are mapped) fall back to fewer tiles per micro-batch
+        for (;;) {
+            ws->cap16_tiles = 0; ws->cap16_T = 0;
+            const size_t nt = (size_t)mb_tiles;
+            int rc;
+            if (!((rc = ws16_alloc(m, (void**)&ws->w16, dr_t16_wimg_bytes(Ml))) || (rc = ws16_alloc(m, (void**)&ws->whT16, dr_t16_whT_bytes(Ml))) ||
+                  (rc = ws16_alloc(m, (void**)&ws->x16, (size_t)T * nt * drt16::kColBlk)) ||
+                  (rc = ws16_alloc(m, (void**)&ws->gate16, (size_t)2 * Ml * T * nt * drt16::kGateImg)) ||
+                  (rc = ws16_alloc(m, (void**)&ws->h16, (size_t)2 * Ml * T * nt * drt16::kHImg)) ||
+                  (rc = ws16_alloc(m, (void**)&ws->zero16, drt16::kColBlk)) ||
+                  (rc = ws16_alloc(m, (void**)&ws->S16, (size_t)T * DR_2H * nt * 128 * sizeof(float))) ||
+                  (rc = ws16_alloc(m, (void**)&ws->P16, (size_t)T * nt * ngrp * 4 * 16 * 128 * sizeof(float))) ||
+                  (rc = ws16_alloc(m, (void**)&ws->dy16, (size_t)nt * 128 * T * Ml * DR_Q * sizeof(float))) ||
+                  (rc = ws16_alloc(m, (void**)&ws->gbar16, (size_t)nt * 128 * T * DR_2H * sizeof(float))) ||
+                  (rc = ws16_alloc(m, (void**)&ws->Px16, (size_t)2 * Ml * 3 * DR_H * F * sizeof(float))) ||
+                  (rc = ws_alloc(m, &ws->dmask, (size_t)Ml * F))))
+                break;
+            cudaGetLastError();
+            void** all16[] = {(void**)&ws->w16, (void**)&ws->whT16, (void**)&ws->x16, (void**)&ws->gate16, (void**)&ws->h16, (void**)&ws->zero16,
+                              (void**)&ws->S16, (void**)&ws->P16, (void**)&ws->dy16, (void**)&ws->gbar16, (void**)&ws->Px16};
+            for (void** pp : all16) if (*pp) { cudaFree(*pp); *pp = nullptr; }
+            if (mb_tiles == 1) return rc;
+            mb_tiles = (mb_tiles + 1) / 2;
+        }
         DR_CUDA(m, cudaMemsetAsync(ws->zero16, 0, drt16::kColBlk, m->stream));
         ws->cap16_tiles = mb_tiles; ws->cap16_T = T;
     }
+    const int Bm = std::min(B, mb_tiles * 128);
     DR_CUDA(m, cudaMemsetAsync(ws->Px16, 0, (size_t)2 * Ml * 3 * DR_H * F * sizeof(float), m->stream));
     DR_CUDA(m, cudaMemsetAsync(ws->dmask, 0, (size_t)Ml * F * sizeof(float), m->stream));
     int rc = dr_t16_pack_weights(m, ws->w16);
@@ -620,6 +631,7 @@ int dr_train_begin_impl(dr_model* m, const float* x, const float* y, int B, int 
     }
     int Bm = (int)std::min<size_t>((size_t)B, std::max<size_t>(1, budget / std::max<size_t>(per_window, 1)));
     if (const char* ov = getenv("DR_TRAIN_MICROBATCH")) { int v = atoi(ov); if (v >= 1) Bm = std::min(B, v); }   // test hook
+    if (m->train_mb >= 1) Bm = std::min(B, m->train_mb);
     dr_train_ws* ws = reinterpret_cast<dr_train_ws*>(m->train_ws);
     if (!ws) { ws = new dr_train_ws(); memset(ws, 0, sizeof(*ws)); m->train_ws = ws; }
     if (ws->stage != TS_IDLE) return dr_fail(m, DR_ESTATE, "a training step is already in flight on this handle");
@@ -1071,6 +1083,12 @@ int dr_train_advance(dr_model* m, int32_t* kind, void** ptr, int64_t* count, int
     int rc = dr_train_advance_impl(m, &k, &p, &c, &dt);
     *kind = k; *ptr = p; *count = c; *dtype = dt;
     return rc;
+}
+
+int dr_train_set_microbatch(dr_model* m, int32_t windows) {
+    if (!m || windows < 0) return DR_EINVAL;
+    m->train_mb = windows;
+    return DR_OK;
 }
 
 int dr_get_grads(dr_model* m, float* host_blob, size_t n) {

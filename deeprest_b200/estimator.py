@@ -94,6 +94,17 @@ class QuantileRNN:
 
     # ---- lifecycle -------------------------------------------------------------------
     def close(self):
+        """Frees the handle.  For an expert-sharded handle that has run the library's exchange this is COLLECTIVE: every rank
+        unmaps its peers' arenas, the ranks synchronise, then the memory is freed (CUDA IPC teardown rule)."""
+        if getattr(self, "_h", None) and self._h.value and getattr(self, "_comm_shape", None):
+            self._lib.dr_comm_detach(self._h)
+            self._comm_shape = None
+            try:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.barrier(group=self._pg)
+            except Exception:
+                pass
         if getattr(self, "_h", None) and self._h.value:
             self._lib.dr_destroy(self._h)
             self._h = C.c_void_p()
@@ -178,6 +189,9 @@ class QuantileRNN:
         """Collective: size this rank's arena for calls up to [max_windows, seq_len] and map the peers' arenas (CUDA IPC
         handles exchanged through the process group — the only thing torch.distributed does for the forward)."""
         import torch.distributed as dist
+        if getattr(self, "_comm_shape", None):           # re-sizing: nobody may still map the arena that is about to be freed
+            self._lib.dr_comm_detach(self._h)
+            dist.barrier(group=self._pg)
         handle = (C.c_ubyte * 64)()
         _lib.check(self._h, self._lib.dr_comm_init(self._h, int(max_windows), int(seq_len), handle, None))
         handles = [None] * self.world
@@ -388,7 +402,7 @@ class QuantileRNN:
                                                         C.c_uint64(int(seed)), C.c_float(lr), loss.data_ptr(), out.data_ptr()))
         return loss
 
-    def train_step_sharded(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0):
+    def train_step_sharded(self, inputs, labels, lr=1e-3, dropout_mask=None, seed=0, local_labels=False, micro_batch=None):
         """Expert-sharded training step (world > 1).  ``inputs`` [B,T,F] and ``labels`` [B,T,M] are the full tensors
         (replicated); each rank trains its own experts.  The library's step is a state machine that asks for three kinds
         of cross-rank sums (S, the loss scalar, the head adjoint); they run here through torch.distributed on the device
@@ -398,7 +412,10 @@ class QuantileRNN:
         dev = torch.device("cuda", self.device)
         x = torch.as_tensor(inputs, dtype=torch.float32).to(dev).contiguous()
         lo, hi = self.rank * self.m_local, (self.rank + 1) * self.m_local
-        y = torch.as_tensor(labels, dtype=torch.float32)[:, :, lo:hi].to(dev).contiguous()
+        if local_labels:                                  # labels already hold only this rank's columns [B,T,M_loc]
+            y = torch.as_tensor(labels, dtype=torch.float32).to(dev).contiguous()
+        else:
+            y = torch.as_tensor(labels, dtype=torch.float32)[:, :, lo:hi].to(dev).contiguous()
         B, T, _ = x.shape
         mask = None
         if dropout_mask is not None:
@@ -406,6 +423,12 @@ class QuantileRNN:
         loss = torch.zeros((), device=dev, dtype=torch.float32)
         out = torch.empty((B, T, self.m_local, layout.Q), device=dev, dtype=torch.float32)
         self._bind_stream()
+        # every rank must cut the batch into the same micro-batches (the cross-rank sums are per micro-batch): a size taken
+        # from each rank's own free memory could differ, so sharded steps use an explicit one (default 128 windows = one tile)
+        if micro_batch is None and "DR_TRAIN_MICROBATCH" not in __import__("os").environ:
+            micro_batch = 128
+        if micro_batch is not None:
+            _lib.check(self._h, self._lib.dr_train_set_microbatch(self._h, int(micro_batch)))
         _lib.check(self._h, self._lib.dr_train_begin_dev(self._h, x.data_ptr(), y.data_ptr(), B, T,
                                                          mask.data_ptr() if mask is not None else None,
                                                          C.c_uint64(int(seed)), C.c_float(lr), loss.data_ptr(), out.data_ptr()))
@@ -421,6 +444,7 @@ class QuantileRNN:
                 break
             t = torch.as_tensor(_Buf(ptr.value, count.value, dtype.value == 1), device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self._pg)
+        self._last_loss_tensor = loss
         return float(loss.item())
 
     def grads(self):

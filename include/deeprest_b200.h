@@ -152,6 +152,10 @@ int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int
  *                    sense that every rank must have returned from it before any rank calls dr_comm_attach.
  *   dr_comm_attach : map the peers' arenas — `ipc_handles` = world x 64 bytes in rank order (own entry ignored), or
  *                    `arena_ptrs` = world device pointers of the same process (peer access is enabled here).
+ *   dr_comm_detach : unmap the peers' arenas.  Teardown order across ranks (CUDA IPC rule: an exported allocation must not be
+ *                    freed while an importer still maps it): every rank detaches, the host synchronises the ranks, then
+ *                    every rank calls dr_destroy (or dr_comm_init again).  dr_destroy detaches by itself, which is enough for
+ *                    several handles inside one process.
  *   dr_forward_sharded_dev : x_dev [B,T,F] (replicated) -> *out_dev = the stacked forecasts [B,T,M,Q] in this rank's arena.
  *                    Asynchronous on the handle's stream (dr_set_stream).  The tensor stays valid until the second-next
  *                    sharded forward on this handle (two tensors alternate); copy it if it must live longer.
@@ -162,6 +166,7 @@ int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int
 int64_t dr_comm_arena_bytes(const dr_model* m, int32_t Bmax, int32_t T);
 int  dr_comm_init  (dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out /* 64 bytes, nullable */, void** arena_ptr_out /* nullable */);
 int  dr_comm_attach(dr_model* m, const void* ipc_handles /* nullable */, void* const* arena_ptrs /* nullable */);
+int  dr_comm_detach(dr_model* m);
 int  dr_forward_sharded_dev(dr_model* m, const float* x_dev, int32_t B, int32_t T, float** out_dev);
 int  dr_forward_sharded    (dr_model* m, const float* x_host, int32_t B, int32_t T, float* out_host, float** out_dev);
 /*   Two forwards in flight: dr_forward_sharded_dev makes the handle's stream wait for its result before it returns control of
@@ -195,6 +200,10 @@ int  dr_train_step_dev(dr_model* m, const float* x_dev, const float* y_dev, int3
                        const uint8_t* dropout_mask_dev, uint64_t seed, float lr, float* loss_dev,
                        float* out_dev /* [B,T,M,Q] train-mode forecasts */);
 int  dr_get_grads     (dr_model* m, float* host_blob, size_t n_floats);
+/* Large batches run as micro-batches (exact: gradients add).  By default the size comes from the free device memory; on
+ * expert-sharded handles every rank must use the SAME size (the cross-rank sums are per micro-batch): set it explicitly.
+ * windows == 0 restores the default.  The bf16 engine rounds up to whole 128-window tiles. */
+int  dr_train_set_microbatch(dr_model* m, int32_t windows);
 /* Expert-sharded training (world > 1): the step is a resumable state machine.  dr_train_begin_dev takes the replicated
  * x [B,T,F], this rank's label columns y [B,T,M_loc], the GLOBAL replayed mask (or NULL + seed) and out_dev
  * [B,T,M_loc,Q]; dr_train_advance runs kernels until *kind == 0 (step done: local gradients applied by Adam) or

@@ -89,7 +89,7 @@ def test_two_gpu_sharded_forward_matches_single_gpu(tmp_path, engine, fused):
             assert used == "True", f"peer-write path not used: {why}"
 
 
-def _train_worker(rank, world, port, path):
+def _train_worker(rank, world, port, path, dtype="fp32"):
     import torch
     import torch.distributed as dist
     from deeprest_b200 import QuantileRNN, layout, synth
@@ -102,7 +102,7 @@ def _train_worker(rank, world, port, path):
         x = synth.windows(3, Bt, Tt, Ft, "diurnal")
         y = synth.labels(4, Bt, Tt, Mt)
         dm = (synth.uniform(8, Mt * Bt * Tt * 2 * layout.H) >= 0.5).astype(np.uint8).reshape(Mt, Bt, Tt, 2 * layout.H)
-        model = QuantileRNN(Ft, Mt, device=rank, process_group=dist.group.WORLD)
+        model = QuantileRNN(Ft, Mt, device=rank, process_group=dist.group.WORLD, dtype=dtype)
         model.load_blob(blob)
         loss = model.train_step_sharded(x, y, lr=1e-3, dropout_mask=dm)
         np.savez(f"{path}.{rank}.npz", loss=loss, grads=model.grads(), after=model.blob())
@@ -136,3 +136,28 @@ def test_two_gpu_sharded_train_step_matches_oracle(tmp_path):
         assert np.abs(g - gr).max() <= 5e-6 * np.abs(ref_g).max() + 1e-9, np.abs(g - gr).max()
         w_ref, _, _ = oracle.adam_step(blob[lo:hi], g, np.zeros(hi - lo, np.float32), np.zeros(hi - lo, np.float32), step=1)
         assert np.abs(z["after"][lo:hi] - w_ref).max() <= 3e-7 * max(1.0, np.abs(w_ref).max())
+
+
+def test_two_gpu_sharded_bf16_train_step_matches_oracle(tmp_path):
+    """the bf16 engine's one-pass-per-micro-batch state machine with its three cross-rank sums (S, G-bar, loss)"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deeprest_b200 import layout, synth
+    from oracle import qrnn_numpy as oracle
+    path = str(tmp_path / "tr16")
+    mp.spawn(_train_worker, args=(2, _free_port(), path, "bf16"), nprocs=2, join=True)
+    Mt, Bt, Tt, Ft = 4, 9, 6, 10
+    blob = synth.weights(13, Mt, Ft, 1.5)
+    x = synth.windows(3, Bt, Tt, Ft, "diurnal")
+    y = synth.labels(4, Bt, Tt, Mt)
+    dm = (synth.uniform(8, Mt * Bt * Tt * 2 * layout.H) >= 0.5).astype(np.float32).reshape(Mt, Bt, Tt, 2 * layout.H)
+    ref_loss, _, ref_g = oracle.loss_and_grads(blob, x, y, Mt, Ft, dropout_masks=dm)
+    pe = layout.params_per_expert(Ft)
+    for r in range(2):
+        z = np.load(f"{path}.{r}.npz")
+        assert abs(float(z["loss"]) - float(ref_loss)) < 5e-4
+        lo, hi = r * 2 * pe, (r + 1) * 2 * pe
+        g, gr = z["grads"][lo:hi], ref_g[lo:hi]
+        assert np.abs(g - gr).max() <= 5e-3 * np.abs(ref_g).max(), np.abs(g - gr).max()      # bf16 tolerance (tests/test_gpu_train.py)
