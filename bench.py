@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the BASELINE configs[2] training block (N=1)")
     ap.add_argument("--no-configs3", action="store_true", help="skip the BASELINE configs[3] block (N=8)")
+    ap.add_argument("--configs3", action="store_true", help="run the configs[3] block (1024 services) at this world size too (testing)")
     ap.add_argument("--no-configs4", action="store_true", help="skip the BASELINE configs[4] sharded-training block (N=8)")
     ap.add_argument("--configs4", action="store_true", help="run the configs[4] block at this world size too (testing)")
     ap.add_argument("--train4-services", type=int, default=512)
@@ -641,6 +642,21 @@ def run_ours(args, rank, world, local_rank):
             import traceback
             log("configs4 block failed:\n" + traceback.format_exc())
             blk4 = {"unavailable": repr(exc)}
+    blk3 = None
+    # (before the main measurement: the exchange arena of a device is allocated once per process and reused — the model with
+    #  the most experts must come first, see csrc/dr_comm.cu::GlobalArena)
+    # ---- BASELINE configs[3] (1024 services over 8 GPUs) as a second, labelled block of the same line ----
+    if ((world == 8 and S != 1024) or args.configs3) and not args.no_configs3:
+        r3, f3, e3, xh3 = measure_inference(args, rank, world, dev, 1024, B, T, F, peaks, "configs3")
+        blk = {"metric": METRIC, "value": r3["value"], "unit": UNIT, "ms_per_step": r3["ms_per_step"], "config": r3["config"],
+               "e2e": r3["e2e"], "roofline": r3["roofline"], "gpu_launches": r3["gpu_launches"], "scaling_note":
+               "BASELINE configs[3] itself: 1024 services sharded over 8 GPUs (128 services = 256 experts per GPU)"}
+        if rank == 0 and not args.no_parity:
+            try:
+                blk["mae_vs_reference"] = parity_block(args, 1024, B, T, F, f3, e3, xh3.numpy(), world)
+            except Exception as exc:
+                blk["mae_vs_reference"] = {"unavailable": repr(exc)}
+        blk3 = blk
     res, final, e2e_final, x_host = measure_inference(args, rank, world, dev, S, B, T, F, peaks, "main")
     line = {
         "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": N, "steps": args.steps,
@@ -652,6 +668,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if blk4 is not None:
         line["configs4"] = blk4
+    if blk3 is not None:
+        line["configs3"] = blk3
     if rank == 0:
         M = 2 * S
         cs = None
@@ -669,18 +687,6 @@ def run_ours(args, rank, world, local_rank):
                 line["mae_vs_reference"] = parity_block(args, S, B, T, F, final, e2e_final, x_host.numpy(), world, cs)
             except Exception as exc:
                 line["mae_vs_reference"] = {"unavailable": repr(exc)}
-    # ---- BASELINE configs[3] (1024 services over 8 GPUs) as a second, labelled block of the same line ----
-    if world == 8 and S != 1024 and not args.no_configs3:
-        r3, f3, e3, xh3 = measure_inference(args, rank, world, dev, 1024, B, T, F, peaks, "configs3")
-        blk = {"metric": METRIC, "value": r3["value"], "unit": UNIT, "ms_per_step": r3["ms_per_step"], "config": r3["config"],
-               "e2e": r3["e2e"], "roofline": r3["roofline"], "gpu_launches": r3["gpu_launches"], "scaling_note":
-               "BASELINE configs[3] itself: 1024 services sharded over 8 GPUs (128 services = 256 experts per GPU)"}
-        if rank == 0 and not args.no_parity:
-            try:
-                blk["mae_vs_reference"] = parity_block(args, 1024, B, T, F, f3, e3, xh3.numpy(), world)
-            except Exception as exc:
-                blk["mae_vs_reference"] = {"unavailable": repr(exc)}
-        line["configs3"] = blk
     # ---- BASELINE configs[2]: the training step (one GPU) ----
     if world == 1 and not args.no_train:
         try:

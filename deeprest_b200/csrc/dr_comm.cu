@@ -25,13 +25,27 @@ namespace {
 constexpr int kMaxWorld = 8, kMaxChunks = 64, kChunk = 256, kRing = 256;
 typedef CUresult (*PFN_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
+// One arena per device and process, kept until the process exits.  On this driver (580.x) a large cudaMalloc issued after a
+// CUDA-IPC mapping has been opened AND closed in the same process fails with cudaErrorAlreadyMapped, so arenas and peer
+// mappings are never released: a later model on the same device (e.g. a second, larger estimator) reuses the arena if it
+// fits — create the model with the largest [Bmax, T, M] first, or set DR_COMM_ARENA_GB.  Epochs are per arena, so flags left
+// by an earlier model are always older than any new forward's.
+struct GlobalArena {
+    uint8_t* base; size_t bytes;
+    uint8_t* peer[kMaxWorld]; bool ipc_open[kMaxWorld]; bool have_peers;
+    cudaIpcMemHandle_t handle; bool have_handle;
+    unsigned int epoch;
+    int world, rank;
+};
+GlobalArena g_arena[64];
+
 struct DrComm {
     int world, rank, Bmax, T, nch_max;
     bool attached;
+    GlobalArena* ga;
     uint8_t* arena; size_t bytes;
-    uint8_t* peer[kMaxWorld]; bool ipc_open[kMaxWorld];
+    uint8_t* peer[kMaxWorld];
     size_t off_S, s_slot, off_out, out_set;
-    unsigned int epoch;
     cudaStream_t cs, ss, xs, os, ds;               // recurrence | S sends | head kernels | forecast scatter | D2H (host entry)
     cudaEvent_t ev_call, ev_done[2], ev_k2[kMaxChunks], ev_x, ev_xs_end[2], ev_ss_end[2], ev_os_end[2], ev_d2h;
     unsigned int *tile_count, *tile_flag;          // local, written by the recurrence kernel
@@ -72,9 +86,7 @@ void layout_arena(DrComm* c, int M_total) {
 static void comm_detach(DrComm* c) {
     cudaStream_t sts[] = {c->cs, c->ss, c->xs, c->os, c->ds};
     for (cudaStream_t s : sts) if (s) cudaStreamSynchronize(s);
-    for (int p = 0; p < c->world; ++p)
-        if (c->ipc_open[p] && c->peer[p]) { cudaIpcCloseMemHandle(c->peer[p]); c->ipc_open[p] = false; c->peer[p] = nullptr; }
-    c->attached = false;
+    // the peer mappings belong to the process-wide arena and stay open (see GlobalArena)
 }
 
 void dr_comm_free(dr_model* m) {
@@ -82,7 +94,7 @@ void dr_comm_free(dr_model* m) {
     if (!c) return;
     cudaStream_t sts[] = {c->cs, c->ss, c->xs, c->os, c->ds};
     comm_detach(c);
-    void* ptrs[] = {c->arena, c->tile_count, c->tile_flag, c->d_ring, c->S_full[0], c->S_full[1], c->P_full[0], c->P_full[1],
+    void* ptrs[] = {c->tile_count, c->tile_flag, c->d_ring, c->S_full[0], c->S_full[1], c->P_full[0], c->P_full[1],
                     c->out_local[0], c->out_local[1], c->x_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (c->h_ring) cudaFreeHost(c->h_ring);
@@ -126,8 +138,23 @@ int dr_comm_init(dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out, voi
             return dr_fail(m, DR_ECUDA, "cuStreamWaitValue32 is not available from this driver (stream memory operations are required)");
         c->wait32 = reinterpret_cast<PFN_wait32>(fn);
     }
-    DR_CUDA(m, cudaMalloc((void**)&c->arena, c->bytes));
-    DR_CUDA(m, cudaMemset(c->arena, 0, kFlagBytes));
+    {
+        GlobalArena* ga = &g_arena[m->cfg.device & 63];
+        if (ga->base && (ga->world != c->world || ga->rank != c->rank))
+            return dr_fail(m, DR_ESTATE, "this device already holds an arena of a different world/rank in this process");
+        if (ga->base && ga->bytes < c->bytes)
+            return dr_fail(m, DR_ENOMEM, "the process-wide exchange arena of this device (" + std::to_string(ga->bytes >> 20) + " MiB) is smaller than this model needs (" +
+                                         std::to_string(c->bytes >> 20) + " MiB) and cannot be re-allocated once peers have mapped it: create the largest "
+                                         "model first or set DR_COMM_ARENA_GB");
+        if (!ga->base) {
+            size_t want = c->bytes;
+            if (const char* gb = getenv("DR_COMM_ARENA_GB")) { const size_t v = (size_t)atof(gb) << 30; if (v > want) want = v; }
+            DR_CUDA(m, cudaMalloc((void**)&ga->base, want));
+            DR_CUDA(m, cudaMemset(ga->base, 0, kFlagBytes));
+            ga->bytes = want; ga->world = c->world; ga->rank = c->rank; ga->epoch = 0;
+        }
+        c->ga = ga; c->arena = ga->base;
+    }
     DR_CUDA(m, cudaMalloc((void**)&c->tile_count, kMaxChunks * sizeof(unsigned int)));
     DR_CUDA(m, cudaMalloc((void**)&c->tile_flag, kMaxChunks * sizeof(unsigned int)));
     DR_CUDA(m, cudaMemset(c->tile_count, 0, kMaxChunks * sizeof(unsigned int)));
@@ -147,10 +174,9 @@ int dr_comm_init(dr_model* m, int32_t Bmax, int32_t T, void* ipc_handle_out, voi
     for (int i = 0; i < kMaxChunks; ++i) DR_CUDA(m, cudaEventCreateWithFlags(&c->ev_k2[i], cudaEventDisableTiming));
     DR_CUDA(m, cudaDeviceSynchronize());
     if (ipc_handle_out) {
-        cudaIpcMemHandle_t h;
-        DR_CUDA(m, cudaIpcGetMemHandle(&h, c->arena));
+        if (!c->ga->have_handle) { DR_CUDA(m, cudaIpcGetMemHandle(&c->ga->handle, c->arena)); c->ga->have_handle = true; }
         static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
-        memcpy(ipc_handle_out, &h, sizeof(h));
+        memcpy(ipc_handle_out, &c->ga->handle, sizeof(cudaIpcMemHandle_t));
     }
     if (arena_ptr_out) *arena_ptr_out = c->arena;
     return DR_OK;
@@ -162,6 +188,7 @@ int dr_comm_detach(dr_model* m) {
     if (!c) return DR_OK;
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     comm_detach(c);
+    c->attached = false;
     return DR_OK;
 }
 
@@ -173,6 +200,7 @@ int dr_comm_attach(dr_model* m, const void* ipc_handles, void* const* arena_ptrs
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     for (int p = 0; p < c->world; ++p) {
         if (p == c->rank) { c->peer[p] = c->arena; continue; }
+        if (c->ga->peer[p]) { c->peer[p] = c->ga->peer[p]; continue; }      // mapped by an earlier model of this process
         if (arena_ptrs) {
             cudaPointerAttributes at;
             DR_CUDA(m, cudaPointerGetAttributes(&at, arena_ptrs[p]));
@@ -182,14 +210,14 @@ int dr_comm_attach(dr_model* m, const void* ipc_handles, void* const* arena_ptrs
             cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return dr_cuda_fail(m, e, "cudaDeviceEnablePeerAccess");
             cudaGetLastError();
-            c->peer[p] = reinterpret_cast<uint8_t*>(arena_ptrs[p]);
+            c->peer[p] = c->ga->peer[p] = reinterpret_cast<uint8_t*>(arena_ptrs[p]);
         } else {
             cudaIpcMemHandle_t h;
             memcpy(&h, reinterpret_cast<const uint8_t*>(ipc_handles) + (size_t)p * sizeof(h), sizeof(h));
             void* ptr = nullptr;
             DR_CUDA(m, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
-            c->peer[p] = reinterpret_cast<uint8_t*>(ptr);
-            c->ipc_open[p] = true;
+            c->peer[p] = c->ga->peer[p] = reinterpret_cast<uint8_t*>(ptr);
+            c->ga->ipc_open[p] = true;
         }
     }
     c->attached = true;
@@ -216,7 +244,7 @@ int forward_sharded(dr_model* m, const float* x, int B, int T, float** out_dev, 
     const int nloc = Ml * DR_Q, ntot = nloc * world;
     const int nch = (B + kChunk - 1) / kChunk;
     const int Bp = dr_s_rows(B);
-    const unsigned int n = ++c->epoch;
+    const unsigned int n = ++c->ga->epoch;
     const int set = (int)(n & 1u);
     cudaStream_t caller = m->stream;
 
@@ -367,7 +395,7 @@ int dr_forward_sharded_wait(dr_model* m, int32_t ticket) {
     DrComm* c = comm_of(m);
     if (!c || !c->attached) return dr_fail(m, DR_ESTATE, "dr_forward_sharded_wait before dr_comm_init / dr_comm_attach");
     const unsigned int n = (unsigned int)ticket;
-    if (n == 0 || n > c->epoch || c->epoch - n > 1) return dr_fail(m, DR_EINVAL, "dr_forward_sharded_wait: the ticket must be one of the last two forwards");
+    if (n == 0 || n > c->ga->epoch || c->ga->epoch - n > 1) return dr_fail(m, DR_EINVAL, "dr_forward_sharded_wait: the ticket must be one of the last two forwards");
     DR_CUDA(m, cudaSetDevice(m->cfg.device));
     DR_CUDA(m, cudaStreamWaitEvent(m->stream, c->ev_done[n & 1u], 0));
     return DR_OK;
