@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BW_NUM);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = a.ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i];
+    for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = a.ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i] * a.drop.inv_keep;
     if (tid == 0) {
         mbar_init(bar(BW_W_LAND), 1);
         mbar_init(bar(BW_A_READY), 8);
@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                 }
             }
             uint32_t kb16 = 0;
+            const f2 dd0 = mk2(d0, d0), dd1 = mk2(d1, d1), dd2 = mk2(d2, d2), ik2 = mk2(a.drop.inv_keep, a.drop.inv_keep), one2 = mk2(1.0f, 1.0f);
 #pragma unroll
             for (int c8 = 0; c8 < 8; ++c8) {                    // 8 hidden units per group = one 16-byte chunk per array
                 LoadSet nxt = cur;
@@ -140,32 +141,30 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                 const float gbv[8] = {cur.g0.x, cur.g0.y, cur.g0.z, cur.g0.w, cur.g1.x, cur.g1.y, cur.g1.z, cur.g1.w};
                 uint32_t par[4], paz[4], pan[4], pdq[4];
 #pragma unroll
-                for (int v = 0; v < 8; v += 2) {                // dr_gate_bwd_kernel's arithmetic on the bf16-stored activations
-                    const float2 r2 = unpack_bf2(wr[v >> 1]), z2 = unpack_bf2(wz[v >> 1]), n2 = unpack_bf2(wn[v >> 1]);
-                    const float2 q2 = unpack_bf2(wq[v >> 1]), h2 = unpack_bf2(wh[v >> 1]);
-                    float out4[2][4];
-#pragma unroll
-                    for (int w = 0; w < 2; ++w) {
-                        const int u = half * 64 + c8 * 8 + v + w;
-                        // adjoint arriving from the heads: keep/(1-p) * (Ct^T dy + G-bar)
-                        const float sv = (cs[u] * d0 + cs[DR_H + u] * d1 + cs[2 * DR_H + u] * d2 + gbv[v + w]) * a.drop.inv_keep;
-                        const float dvv = ((kb >> (v + w)) & 1u) ? sv : 0.0f;
-                        const float rr = w ? r2.y : r2.x, zz = w ? z2.y : z2.x, nn = w ? n2.y : n2.x, qq = w ? q2.y : q2.x, hp = w ? h2.y : h2.x;
-                        const float dhv = dh[c8 * 8 + v + w] + dvv;
-                        const float dn = dhv * (1.0f - zz);
-                        const float dz = dhv * (hp - nn);
-                        const float dan = dn * (1.0f - nn * nn);
-                        const float dr = dan * qq;
-                        out4[w][0] = dr * rr * (1.0f - rr);     // da_r
-                        out4[w][1] = dz * zz * (1.0f - zz);     // da_z
-                        out4[w][2] = dan;                       // da_n
-                        out4[w][3] = dan * rr;                  // dq
-                        dh[c8 * 8 + v + w] = dhv * zz;          // + dgh W_hh below
-                    }
-                    par[v >> 1] = pack_bf2(out4[0][0], out4[1][0]);
-                    paz[v >> 1] = pack_bf2(out4[0][1], out4[1][1]);
-                    pan[v >> 1] = pack_bf2(out4[0][2], out4[1][2]);
-                    pdq[v >> 1] = pack_bf2(out4[0][3], out4[1][3]);
+                for (int v = 0; v < 8; v += 2) {                // dr_gate_bwd_kernel's arithmetic on the bf16-stored activations,
+                    // two hidden units per instruction (FFMA2 / FMUL2 / FADD2)
+                    const f2 r2 = unpack_bf2p(wr[v >> 1]), z2 = unpack_bf2p(wz[v >> 1]), n2 = unpack_bf2p(wn[v >> 1]);
+                    const f2 q2 = unpack_bf2p(wq[v >> 1]), h2 = unpack_bf2p(wh[v >> 1]);
+                    const int u = half * 64 + c8 * 8 + v;
+                    // adjoint arriving from the heads: keep/(1-p) * (Ct^T dy + G-bar)   (cs is pre-scaled by 1/(1-p))
+                    f2 sv = fma2(*reinterpret_cast<const f2*>(cs + u), dd0, mul2(mk2(gbv[v], gbv[v + 1]), ik2));
+                    sv = fma2(*reinterpret_cast<const f2*>(cs + DR_H + u), dd1, sv);
+                    sv = fma2(*reinterpret_cast<const f2*>(cs + 2 * DR_H + u), dd2, sv);
+                    const f2 km = mk2(((kb >> v) & 1u) ? 1.0f : 0.0f, ((kb >> (v + 1)) & 1u) ? 1.0f : 0.0f);
+                    const f2 dhv = fma2(sv, km, mk2(dh[c8 * 8 + v], dh[c8 * 8 + v + 1]));
+                    const f2 omz = sub2(one2, z2);
+                    const f2 dn = mul2(dhv, omz);
+                    const f2 dz = mul2(dhv, sub2(h2, n2));
+                    const f2 dan = mul2(dn, sub2(one2, mul2(n2, n2)));
+                    const f2 dr = mul2(dan, q2);
+                    const f2 dar = mul2(mul2(dr, r2), sub2(one2, r2));
+                    const f2 daz = mul2(mul2(dz, z2), omz);
+                    const f2 dqq = mul2(dan, r2);
+                    un2(mul2(dhv, z2), dh[c8 * 8 + v], dh[c8 * 8 + v + 1]);     // + dgh W_hh below
+                    par[v >> 1] = pack_bf2p(dar);
+                    paz[v >> 1] = pack_bf2p(daz);
+                    pan[v >> 1] = pack_bf2p(dan);
+                    pdq[v >> 1] = pack_bf2p(dqq);
                 }
                 // adjoints back into the gate image, in place (dead rows stay zero: every input of theirs is zero)
                 const uint32_t o = img_off(row, c8);

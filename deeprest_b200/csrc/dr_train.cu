@@ -428,19 +428,18 @@ __global__ void dr_adam_kernel(float* __restrict__ w, const float* __restrict__ 
 __global__ void dr_finish_loss_kernel(const double* acc, double inv_n, float* loss) { *loss = (float)(*acc * inv_n); }
 
 // bf16 engine: head weight gradients from the h images.  U[e][q][k] = sum_{t,b} dy r~ ; V = sum dy S ; db = sum dy
-// (dC = U, dA = (V - U)/(M-1); qrnn.py:46-54 differentiated).  grid (M_loc, row chunks); a thread owns 4 consecutive columns k
-// of [fwd | rev] (one 8-byte h load, one float4 of S in its k-group-major layout, one dropout hash) and every 4th row of the
-// chunk; rows are walked window-fastest, so the 4 row slots of a block read 64 contiguous bytes of S per k-group.
+// (dC = U, dA = (V - U)/(M-1); qrnn.py:46-54 differentiated).  grid (M_loc, chunks of time steps); a thread owns 4 consecutive
+// columns k of [fwd | rev] (one 8-byte h load, one float4 of S in its k-group-major layout, one dropout hash) and every 4th
+// window; the loops run over (step, 128-window tile, window) so that every address is a base plus a constant stride.
 __global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __restrict__ himg, const float* __restrict__ S, const float* __restrict__ dy,
                                                               drt16::Drop drop, float* __restrict__ gblob, int off_hw, int off_hb, int pe, float inv_m1,
-                                                              int M_loc, int e_lo, int Bfull, int b0, int Bm, int T, int rows_per_chunk) {
+                                                              int M_loc, int e_lo, int Bfull, int b0, int Bm, int T, int steps_per_chunk) {
     __shared__ float red[3][2][3][256];               // [slot 1..3][u|v][q][k]
+    __shared__ float redb[4][3];
     const int e = blockIdx.x, kg = threadIdx.x & 63, slot = threadIdx.x >> 6;
     const int k0 = kg * 4, d = k0 >> 7, j0 = k0 & 127;
     const int ntiles = (Bm + 127) >> 7, Bp = ntiles * 128;
-    const size_t rows = (size_t)T * Bm;
-    size_t r0 = (size_t)blockIdx.y * rows_per_chunk, r1 = r0 + rows_per_chunk;
-    if (r1 > rows) r1 = rows;
+    const int t0 = blockIdx.y * steps_per_chunk, t1 = min(T, t0 + steps_per_chunk);
     float u[3][4], v[3][4], sb[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int q = 0; q < 3; ++q)
@@ -448,25 +447,34 @@ __global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __re
         for (int i = 0; i < 4; ++i) { u[q][i] = 0.f; v[q][i] = 0.f; }
     const size_t col_off = (size_t)(j0 >> 6) * drt16::kColBlk + (size_t)(j0 & 7) * 2;
     const int chunk = (j0 & 63) >> 3;
+    const size_t dy_bstride = (size_t)T * M_loc * DR_Q;
+    const size_t drop_bstride = (size_t)T * DR_2H;
+    for (int t = t0; t < t1; ++t) {
+        for (int tile = 0; tile < ntiles; ++tile) {
+            const uint8_t* hblk = himg + drt16::blk_index(d, e, t, tile, M_loc, T, ntiles) * drt16::kHImg + col_off;
+            const float* sblk = S + (((size_t)t * 64 + kg) * Bp + tile * 128) * 4;
+            const int nb = min(128, Bm - tile * 128);
+            const float* dblk = dy + ((size_t)(tile * 128) * T + t) * M_loc * DR_Q + (size_t)e * DR_Q;
+            const size_t dbase = (((size_t)(e_lo + e) * Bfull + b0 + tile * 128) * T + t) * DR_2H + k0;
 #pragma unroll 2
-    for (size_t r = r0 + slot; r < r1; r += 4) {
-        const int t = (int)(r / Bm), b = (int)(r % Bm);
-        const uint8_t* hrow = himg + drt16::blk_index(d, e, t, b >> 7, M_loc, T, ntiles) * drt16::kHImg + col_off + drt16::img_off(b & 127, chunk);
-        const uint2 hw2 = __ldg(reinterpret_cast<const uint2*>(hrow));
-        const float4 s4 = __ldg(reinterpret_cast<const float4*>(S + (((size_t)t * 64 + kg) * Bp + b) * 4));
-        const float* dd = dy + (((size_t)b * T + t) * M_loc + e) * DR_Q;
-        const float g0 = __ldg(dd), g1 = __ldg(dd + 1), g2 = __ldg(dd + 2);
-        const uint32_t kb = drt16::keep4(drop, (((size_t)(e_lo + e) * Bfull + b0 + b) * T + t) * DR_2H + k0);
-        const float2 h01 = drt16::unpack_bf2(hw2.x), h23 = drt16::unpack_bf2(hw2.y);
-        const float rt[4] = {(kb & 1u) ? h01.x * drop.inv_keep : 0.f, (kb & 2u) ? h01.y * drop.inv_keep : 0.f,
-                             (kb & 4u) ? h23.x * drop.inv_keep : 0.f, (kb & 8u) ? h23.y * drop.inv_keep : 0.f};
-        const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
-        const float gq[3] = {g0, g1, g2};
+            for (int r = slot; r < nb; r += 4) {
+                const uint2 hw2 = __ldg(reinterpret_cast<const uint2*>(hblk + drt16::img_off(r, chunk)));
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(sblk + (size_t)r * 4));
+                const float* dd = dblk + (size_t)r * dy_bstride;
+                const float g0 = __ldg(dd), g1 = __ldg(dd + 1), g2 = __ldg(dd + 2);
+                const uint32_t kb = drt16::keep4(drop, dbase + (size_t)r * drop_bstride);
+                const float2 h01 = drt16::unpack_bf2(hw2.x), h23 = drt16::unpack_bf2(hw2.y);
+                const float rt[4] = {(kb & 1u) ? h01.x * drop.inv_keep : 0.f, (kb & 2u) ? h01.y * drop.inv_keep : 0.f,
+                                     (kb & 4u) ? h23.x * drop.inv_keep : 0.f, (kb & 8u) ? h23.y * drop.inv_keep : 0.f};
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+                const float gq[3] = {g0, g1, g2};
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < 3; ++q) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { u[q][i] = fmaf(gq[q], rt[i], u[q][i]); v[q][i] = fmaf(gq[q], sv[i], v[q][i]); }
-            if (kg == 0) sb[q] += gq[q];
+                    for (int i = 0; i < 4; ++i) { u[q][i] = fmaf(gq[q], rt[i], u[q][i]); v[q][i] = fmaf(gq[q], sv[i], v[q][i]); }
+                    if (kg == 0) sb[q] += gq[q];
+                }
+            }
         }
     }
     if (slot > 0) {
@@ -475,7 +483,6 @@ __global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __re
 #pragma unroll
             for (int i = 0; i < 4; ++i) { red[slot - 1][0][q][k0 + i] = u[q][i]; red[slot - 1][1][q][k0 + i] = v[q][i]; }
     }
-    __shared__ float redb[4][3];
     if (kg == 0) { redb[slot][0] = sb[0]; redb[slot][1] = sb[1]; redb[slot][2] = sb[2]; }
     __syncthreads();
     if (slot == 0) {
@@ -974,8 +981,8 @@ static int train_advance_inner(dr_model* m, int* kind, void** ptr, long long* co
             rc = dr_launch_wgrad16(m, ws->gate16, ws->h16, ws->x16, ws->zero16, ws->Px16, bm, T);
             if (rc) return rc;
             if (Ml) {
-                const int chunk = 2048;
-                dim3 grid(Ml, (unsigned)(((size_t)T * bm + chunk - 1) / chunk));
+                const int chunk = std::max(1, 2048 / std::max(bm, 1));              // time steps per CTA (~2048 rows)
+                dim3 grid(Ml, (unsigned)((T + chunk - 1) / chunk));
                 drt16::Drop dp;
                 dp.mask = ws->mask; dp.seed = ws->seed; dp.inv_keep = 1.0f / (1.0f - p); dp.thr16 = (uint32_t)(p * 65536.0f + 0.5f);
                 dr_head_grad16_kernel<<<grid, 256, 0, st>>>(ws->h16, ws->S16, ws->dy16, dp, m->d_grad, m->off.head_w, m->off.head_b, pe,
