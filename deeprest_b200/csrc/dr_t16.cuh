@@ -41,14 +41,7 @@ __device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
     return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
 
-// ---- packed fp32 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 — two fp32 lanes per instruction, half the issue slots) ----
-struct f2 { unsigned long long v; };
-__device__ __forceinline__ f2 mk2(float a, float b) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void un2(f2 a, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); }
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f2 sub2(f2 a, f2 b) { f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+using drtc::f2; using drtc::mk2; using drtc::un2; using drtc::fma2; using drtc::mul2; using drtc::add2; using drtc::sub2;
 __device__ __forceinline__ f2 unpack_bf2p(uint32_t u) { return mk2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)); }
 __device__ __forceinline__ uint32_t pack_bf2p(f2 a) { float x, y; un2(a, x, y); return pack_bf2(x, y); }
 
