@@ -431,16 +431,27 @@ def train_sharded_block(args, rank, world, dev, peaks):
 # --------------------------------------------------------------------------- our arm
 def shared_host_tensor(shape, rank, world, tag):
     """One pinned host tensor shared by the ranks of this box (POSIX shared memory): every rank's D2H lands in its own
-    columns of the same [B,T,M,Q] array."""
+    columns of the same [B,T,M,Q] array.  Falls back to a private pinned tensor per rank when /dev/shm is too small."""
     import torch
     import torch.distributed as dist
     n = int(np.prod(shape)) * 4
     path = f"/dev/shm/deeprest_b200_{tag}_{os.environ.get('MASTER_PORT', '0')}"
+    ok = torch.zeros(1, device="cuda")
     if rank == 0:
-        with open(path, "wb") as f:
-            f.truncate(n)
+        try:
+            st = os.statvfs("/dev/shm")
+            if st.f_bavail * st.f_frsize < n + (64 << 20):
+                raise OSError("not enough space in /dev/shm")
+            with open(path, "wb") as f:
+                f.truncate(n)
+            ok += 1
+        except OSError as exc:
+            log(f"shared host tensor unavailable ({exc}); every rank uses a private pinned tensor")
     if world > 1:
-        dist.barrier()
+        dist.broadcast(ok, 0)
+    if float(ok.item()) < 1:
+        t = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+        return t.numpy(), True, False
     arr = np.memmap(path, dtype=np.float32, mode="r+", shape=tuple(shape))
     rt = torch.cuda.cudart()
     rc = rt.cudaHostRegister(arr.ctypes.data, n, 0)
@@ -449,7 +460,7 @@ def shared_host_tensor(shape, rank, world, tag):
         dist.barrier()
     if rank == 0:
         os.unlink(path)                                        # the mappings keep it alive
-    return arr, pinned
+    return arr, pinned, True
 
 
 def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
@@ -535,9 +546,9 @@ def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
     x_np = x_host.numpy()
     if world == 1:
         out_host = torch.empty((B, T, M, layout.Q), dtype=torch.float32, pin_memory=True)
-        out_np, pinned = out_host.numpy(), True
+        out_np, pinned, shared = out_host.numpy(), True, False
     else:
-        out_np, pinned = shared_host_tensor((B, T, M, layout.Q), rank, world, tag)
+        out_np, pinned, shared = shared_host_tensor((B, T, M, layout.Q), rank, world, tag)
     d2h = B * T * M_loc * layout.Q * 4
 
     def e2e_step():
@@ -575,7 +586,7 @@ def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
            "roofline": roofline, "batches_in_flight": 1 if world == 1 else 2,
            "e2e": {"value": S * B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                    "ms_per_step": e2e_s * 1e3, "per_rank": {"h2d_bytes": h2d, "d2h_bytes": d2h},
-                   "host_output_pinned": bool(pinned),
+                   "host_output_pinned": bool(pinned), "host_output_shared_by_ranks": bool(shared),
                    "note": ("C-ABI dr_forward with pinned host buffers" if world == 1 else
                             "C-ABI dr_forward_sharded per rank: x (replicated) H2D, and every rank's own forecast columns D2H into one "
                             "shared pinned host tensor [B,T,M,Q], chunk by chunk under the compute")}}
