@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BW_NUM);
     auto bar = [&](int i) { return smem_u32(&bars[i]); };
-    for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = a.ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i] * a.drop.inv_keep;
+    for (int i = tid; i < DR_Q * DR_H; i += kThreads) cs[i] = a.ct[(size_t)(e * 2 + dir) * DR_Q * DR_H + i];
     if (tid == 0) {
         mbar_init(bar(BW_W_LAND), 1);
         mbar_init(bar(BW_A_READY), 8);
@@ -78,107 +78,105 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
 #pragma unroll
         for (int j = 0; j < 64; ++j) dh[j] = 0.0f;
         uint32_t d_phase = 0;
-        // One step's inputs are consumed 8 hidden units at a time; the loads of the NEXT group (and, at the end of a step, of the
-        // next step's first group) are issued before the current group's arithmetic, so the ~700-cycle L2 latency of each group
-        // hides behind the previous one instead of stalling the warp eight times per step (ncu r02: 40 % long-scoreboard stalls).
-        struct LoadSet { uint4 r, z, n, q, h; float4 g0, g1; };
-        struct StepPtr { uint8_t* gimg; const uint8_t* hpim; const float* gb; const float* dd; int t; bool has_h; };
-        auto step_ptr = [&](int s) {
-            StepPtr p;
-            p.t = dir ? (T - 1 - s) : s;
-            const int tp = dir ? p.t + 1 : p.t - 1;            // the step whose output was this step's h_prev
-            p.has_h = s > 0;
-            p.gimg = a.gate + blk_index(dir, e, p.t, tile, a.M_loc, T, a.ntiles) * kGateImg + (size_t)half * kColBlk;
-            p.hpim = a.himg + blk_index(dir, e, s > 0 ? tp : p.t, tile, a.M_loc, T, a.ntiles) * kHImg + (size_t)half * kColBlk;
-            p.gb = a.gbar + (bb * T + p.t) * DR_2H + dir * DR_H + half * 64;
-            p.dd = a.dy + ((bb * T + p.t) * a.M_loc + e) * DR_Q;
-            return p;
-        };
-        auto load_set = [&](const StepPtr& p, int c8) {
-            LoadSet L;
-            const uint32_t o = img_off(row, c8);
-            L.r = *reinterpret_cast<const uint4*>(p.gimg + o);
-            L.z = *reinterpret_cast<const uint4*>(p.gimg + 2 * kColBlk + o);
-            L.n = *reinterpret_cast<const uint4*>(p.gimg + 4 * kColBlk + o);
-            L.q = *reinterpret_cast<const uint4*>(p.gimg + 6 * kColBlk + o);
-            L.h = make_uint4(0, 0, 0, 0);
-            if (p.has_h) L.h = __ldg(reinterpret_cast<const uint4*>(p.hpim + o));
-            L.g0 = make_float4(0.f, 0.f, 0.f, 0.f); L.g1 = L.g0;
-            if (live) { L.g0 = __ldg(reinterpret_cast<const float4*>(p.gb + c8 * 8)); L.g1 = __ldg(reinterpret_cast<const float4*>(p.gb + c8 * 8 + 4)); }
-            return L;
-        };
-        StepPtr sp = step_ptr(T - 1);
-        LoadSet cur = load_set(sp, 0);
-        float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-        if (live) { d0 = __ldg(sp.dd); d1 = __ldg(sp.dd + 1); d2 = __ldg(sp.dd + 2); }
         for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
-            StepPtr nsp = sp;
-            float nd0 = 0.f, nd1 = 0.f, nd2 = 0.f;
-            if (s > 0) {
-                nsp = step_ptr(s - 1);
-                if (live) { nd0 = __ldg(nsp.dd); nd1 = __ldg(nsp.dd + 1); nd2 = __ldg(nsp.dd + 2); }
-                if (s > 1) {                                    // two steps ahead: warm L2 (one 128-byte row per array)
-                    const StepPtr fp = step_ptr(s - 2);
-                    const uint32_t ro = img_off(row, 0) & ~127u;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) prefetch_l2(fp.gimg + (size_t)g * 2 * kColBlk + ro);
-                    if (fp.has_h) prefetch_l2(fp.hpim + ro);
-                    if (live) { prefetch_l2(fp.gb); prefetch_l2(fp.gb + 32); }
-                }
+            const int t = dir ? (T - 1 - s) : s;
+            const int tp = dir ? t + 1 : t - 1;                 // the step whose output was this step's h_prev
+            uint8_t* gimg = a.gate + blk_index(dir, e, t, tile, a.M_loc, T, a.ntiles) * kGateImg + (size_t)half * kColBlk;
+            const uint8_t* hpim = a.himg + blk_index(dir, e, s > 0 ? tp : t, tile, a.M_loc, T, a.ntiles) * kHImg + (size_t)half * kColBlk;
+            const float* gb = a.gbar + (bb * T + t) * DR_2H + dir * DR_H + half * 64;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (live) {
+                const float* dd = a.dy + ((bb * T + t) * a.M_loc + e) * DR_Q;
+                d0 = dd[0]; d1 = dd[1]; d2 = dd[2];
             }
-            uint32_t kb16 = 0;
-            const f2 dd0 = mk2(d0, d0), dd1 = mk2(d1, d1), dd2 = mk2(d2, d2), ik2 = mk2(a.drop.inv_keep, a.drop.inv_keep), one2 = mk2(1.0f, 1.0f);
+            if (s > 0) {                                        // next iteration's rows (step tp): warm L2 while this step runs
+                const long long nb = (long long)(dir ? 1 : -1) * (long long)a.ntiles;
+                const uint32_t ro = img_off(row, 0) & ~127u;                     // this window's 128-byte row
+                const uint8_t* gnext = gimg + nb * (long long)kGateImg + ro;
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {                    // 8 hidden units per group = one 16-byte chunk per array
-                LoadSet nxt = cur;
-                if (c8 < 7) nxt = load_set(sp, c8 + 1);
-                else if (s > 0) nxt = load_set(nsp, 0);
-                if ((c8 & 1) == 0) kb16 = live ? keep16(a.drop, drop_base + (size_t)sp.t * DR_2H + c8 * 8) : 0u;
-                const uint32_t kb = (c8 & 1) ? (kb16 >> 8) : kb16;
-                const uint32_t wr[4] = {cur.r.x, cur.r.y, cur.r.z, cur.r.w}, wz[4] = {cur.z.x, cur.z.y, cur.z.z, cur.z.w};
-                const uint32_t wn[4] = {cur.n.x, cur.n.y, cur.n.z, cur.n.w}, wq[4] = {cur.q.x, cur.q.y, cur.q.z, cur.q.w};
-                const uint32_t wh[4] = {cur.h.x, cur.h.y, cur.h.z, cur.h.w};
-                const float gbv[8] = {cur.g0.x, cur.g0.y, cur.g0.z, cur.g0.w, cur.g1.x, cur.g1.y, cur.g1.z, cur.g1.w};
-                uint32_t par[4], paz[4], pan[4], pdq[4];
+                for (int g = 0; g < 4; ++g) prefetch_l2(gnext + (size_t)g * 2 * kColBlk);
+                if (s > 1) prefetch_l2(hpim + nb * (long long)kHImg + ro);
+                if (live) { prefetch_l2(gb + (long long)(dir ? 1 : -1) * DR_2H); prefetch_l2(gb + (long long)(dir ? 1 : -1) * DR_2H + 32); }
+            }
 #pragma unroll
-                for (int v = 0; v < 8; v += 2) {                // dr_gate_bwd_kernel's arithmetic on the bf16-stored activations,
-                    // two hidden units per instruction (FFMA2 / FMUL2 / FADD2)
-                    const f2 r2 = unpack_bf2p(wr[v >> 1]), z2 = unpack_bf2p(wz[v >> 1]), n2 = unpack_bf2p(wn[v >> 1]);
-                    const f2 q2 = unpack_bf2p(wq[v >> 1]), h2 = unpack_bf2p(wh[v >> 1]);
-                    const int u = half * 64 + c8 * 8 + v;
-                    // adjoint arriving from the heads: keep/(1-p) * (Ct^T dy + G-bar)   (cs is pre-scaled by 1/(1-p))
-                    f2 sv = fma2(*reinterpret_cast<const f2*>(cs + u), dd0, mul2(mk2(gbv[v], gbv[v + 1]), ik2));
-                    sv = fma2(*reinterpret_cast<const f2*>(cs + DR_H + u), dd1, sv);
-                    sv = fma2(*reinterpret_cast<const f2*>(cs + 2 * DR_H + u), dd2, sv);
-                    const f2 km = mk2(((kb >> v) & 1u) ? 1.0f : 0.0f, ((kb >> (v + 1)) & 1u) ? 1.0f : 0.0f);
-                    const f2 dhv = fma2(sv, km, mk2(dh[c8 * 8 + v], dh[c8 * 8 + v + 1]));
-                    const f2 omz = sub2(one2, z2);
-                    const f2 dn = mul2(dhv, omz);
-                    const f2 dz = mul2(dhv, sub2(h2, n2));
-                    const f2 dan = mul2(dn, sub2(one2, mul2(n2, n2)));
-                    const f2 dr = mul2(dan, q2);
-                    const f2 dar = mul2(mul2(dr, r2), sub2(one2, r2));
-                    const f2 daz = mul2(mul2(dz, z2), omz);
-                    const f2 dqq = mul2(dan, r2);
-                    un2(mul2(dhv, z2), dh[c8 * 8 + v], dh[c8 * 8 + v + 1]);     // + dgh W_hh below
-                    par[v >> 1] = pack_bf2p(dar);
-                    paz[v >> 1] = pack_bf2p(daz);
-                    pan[v >> 1] = pack_bf2p(dan);
-                    pdq[v >> 1] = pack_bf2p(dqq);
+            for (int c = 0; c < 4; ++c) {                       // 16 hidden units at a time = two 16-byte chunks per array
+                const uint32_t o0 = img_off(row, 2 * c), o1 = img_off(row, 2 * c + 1);
+                uint32_t wr[8], wz[8], wn[8], wq[8], wh[8];
+                {
+                    const uint4 r0 = *reinterpret_cast<const uint4*>(gimg + o0), r1 = *reinterpret_cast<const uint4*>(gimg + o1);
+                    const uint4 z0 = *reinterpret_cast<const uint4*>(gimg + 2 * kColBlk + o0), z1 = *reinterpret_cast<const uint4*>(gimg + 2 * kColBlk + o1);
+                    const uint4 n0 = *reinterpret_cast<const uint4*>(gimg + 4 * kColBlk + o0), n1 = *reinterpret_cast<const uint4*>(gimg + 4 * kColBlk + o1);
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(gimg + 6 * kColBlk + o0), q1 = *reinterpret_cast<const uint4*>(gimg + 6 * kColBlk + o1);
+                    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+                    if (s > 0) { h0 = __ldg(reinterpret_cast<const uint4*>(hpim + o0)); h1 = __ldg(reinterpret_cast<const uint4*>(hpim + o1)); }
+                    wr[0] = r0.x; wr[1] = r0.y; wr[2] = r0.z; wr[3] = r0.w; wr[4] = r1.x; wr[5] = r1.y; wr[6] = r1.z; wr[7] = r1.w;
+                    wz[0] = z0.x; wz[1] = z0.y; wz[2] = z0.z; wz[3] = z0.w; wz[4] = z1.x; wz[5] = z1.y; wz[6] = z1.z; wz[7] = z1.w;
+                    wn[0] = n0.x; wn[1] = n0.y; wn[2] = n0.z; wn[3] = n0.w; wn[4] = n1.x; wn[5] = n1.y; wn[6] = n1.z; wn[7] = n1.w;
+                    wq[0] = q0.x; wq[1] = q0.y; wq[2] = q0.z; wq[3] = q0.w; wq[4] = q1.x; wq[5] = q1.y; wq[6] = q1.z; wq[7] = q1.w;
+                    wh[0] = h0.x; wh[1] = h0.y; wh[2] = h0.z; wh[3] = h0.w; wh[4] = h1.x; wh[5] = h1.y; wh[6] = h1.z; wh[7] = h1.w;
+                }
+                // adjoint arriving from the heads for these 16 units: keep/(1-p) * (Ct^T dy + G-bar)
+                float dv[16];
+                {
+                    const uint32_t kb = live ? keep16(a.drop, drop_base + (size_t)t * DR_2H + c * 16) : 0u;
+#pragma unroll
+                    for (int v = 0; v < 16; v += 4) {
+                        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) g4 = __ldg(reinterpret_cast<const float4*>(gb + c * 16 + v));
+                        const int u = half * 64 + c * 16 + v;
+                        const float4 c0 = *reinterpret_cast<const float4*>(cs + u);
+                        const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u);
+                        const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u);
+                        const float s0 = (c0.x * d0 + c1.x * d1 + c2.x * d2 + g4.x) * a.drop.inv_keep;
+                        const float s1 = (c0.y * d0 + c1.y * d1 + c2.y * d2 + g4.y) * a.drop.inv_keep;
+                        const float s2 = (c0.z * d0 + c1.z * d1 + c2.z * d2 + g4.z) * a.drop.inv_keep;
+                        const float s3 = (c0.w * d0 + c1.w * d1 + c2.w * d2 + g4.w) * a.drop.inv_keep;
+                        dv[v] = ((kb >> v) & 1u) ? s0 : 0.0f;
+                        dv[v + 1] = ((kb >> (v + 1)) & 1u) ? s1 : 0.0f;
+                        dv[v + 2] = ((kb >> (v + 2)) & 1u) ? s2 : 0.0f;
+                        dv[v + 3] = ((kb >> (v + 3)) & 1u) ? s3 : 0.0f;
+                    }
+                }
+                uint32_t par[8], paz[8], pan[8], pdq[8];
+#pragma unroll
+                for (int v = 0; v < 16; v += 2) {               // dr_gate_bwd_kernel's arithmetic on the bf16-stored activations
+                    const float2 r2 = unpack_bf2(wr[v >> 1]), z2 = unpack_bf2(wz[v >> 1]), n2 = unpack_bf2(wn[v >> 1]);
+                    const float2 q2 = unpack_bf2(wq[v >> 1]), h2 = unpack_bf2(wh[v >> 1]);
+                    float out4[2][4];
+#pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const float rr = w ? r2.y : r2.x, zz = w ? z2.y : z2.x, nn = w ? n2.y : n2.x, qq = w ? q2.y : q2.x, hp = w ? h2.y : h2.x;
+                        const float dhv = dh[c * 16 + v + w] + dv[v + w];
+                        const float dn = dhv * (1.0f - zz);
+                        const float dz = dhv * (hp - nn);
+                        const float dan = dn * (1.0f - nn * nn);
+                        const float dr = dan * qq;
+                        out4[w][0] = dr * rr * (1.0f - rr);     // da_r
+                        out4[w][1] = dz * zz * (1.0f - zz);     // da_z
+                        out4[w][2] = dan;                       // da_n
+                        out4[w][3] = dan * rr;                  // dq
+                        dh[c * 16 + v + w] = dhv * zz;          // + dgh W_hh below
+                    }
+                    par[v >> 1] = pack_bf2(out4[0][0], out4[1][0]);
+                    paz[v >> 1] = pack_bf2(out4[0][1], out4[1][1]);
+                    pan[v >> 1] = pack_bf2(out4[0][2], out4[1][2]);
+                    pdq[v >> 1] = pack_bf2(out4[0][3], out4[1][3]);
                 }
                 // adjoints back into the gate image, in place (dead rows stay zero: every input of theirs is zero)
-                const uint32_t o = img_off(row, c8);
-                *reinterpret_cast<uint4*>(sp.gimg + o) = make_uint4(par[0], par[1], par[2], par[3]);
-                *reinterpret_cast<uint4*>(sp.gimg + 2 * kColBlk + o) = make_uint4(paz[0], paz[1], paz[2], paz[3]);
-                *reinterpret_cast<uint4*>(sp.gimg + 4 * kColBlk + o) = make_uint4(pan[0], pan[1], pan[2], pan[3]);
-                *reinterpret_cast<uint4*>(sp.gimg + 6 * kColBlk + o) = make_uint4(pdq[0], pdq[1], pdq[2], pdq[3]);
+                *reinterpret_cast<uint4*>(gimg + o0) = make_uint4(par[0], par[1], par[2], par[3]);
+                *reinterpret_cast<uint4*>(gimg + o1) = make_uint4(par[4], par[5], par[6], par[7]);
+                *reinterpret_cast<uint4*>(gimg + 2 * kColBlk + o0) = make_uint4(paz[0], paz[1], paz[2], paz[3]);
+                *reinterpret_cast<uint4*>(gimg + 2 * kColBlk + o1) = make_uint4(paz[4], paz[5], paz[6], paz[7]);
+                *reinterpret_cast<uint4*>(gimg + 4 * kColBlk + o0) = make_uint4(pan[0], pan[1], pan[2], pan[3]);
+                *reinterpret_cast<uint4*>(gimg + 4 * kColBlk + o1) = make_uint4(pan[4], pan[5], pan[6], pan[7]);
+                *reinterpret_cast<uint4*>(gimg + 6 * kColBlk + o0) = make_uint4(pdq[0], pdq[1], pdq[2], pdq[3]);
+                *reinterpret_cast<uint4*>(gimg + 6 * kColBlk + o1) = make_uint4(pdq[4], pdq[5], pdq[6], pdq[7]);
                 if (s > 0) {                                    // A operand of this step's product: dgh = (da_r, da_z, dq), k = gate*128 + unit
-                    const uint32_t col = (uint32_t)(half * 64 + c8 * 8) / 2;
-                    tmem_st4(tbase + lane_base + kColA + col, par);
-                    tmem_st4(tbase + lane_base + kColA + 64 + col, paz);
-                    tmem_st4(tbase + lane_base + kColA + 128 + col, pdq);
+                    const uint32_t col = (uint32_t)(half * 64 + c * 16) / 2;
+                    tmem_st8(tbase + lane_base + kColA + col, par);
+                    tmem_st8(tbase + lane_base + kColA + 64 + col, paz);
+                    tmem_st8(tbase + lane_base + kColA + 128 + col, pdq);
                 }
-                cur = nxt;
             }
             if (s > 0) {
                 tc_wait_st();
@@ -198,7 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                 }
                 tc_fence_before();                              // D is free again once every warp arrives on A_READY
             }
-            sp = nsp; d0 = nd0; d1 = nd1; d2 = nd2;
         }
     } else {
         // ======================= weight load + MMA issuer (one elected thread of warp 8) =======================

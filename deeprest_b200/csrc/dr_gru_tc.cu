@@ -33,9 +33,6 @@ using namespace drtc;
 
 namespace {
 
-#ifndef DR_TC_PACKED
-#define DR_TC_PACKED 1                 // packed fp32 (FFMA2) arithmetic in the gate epilogue; 0 = the scalar reference form
-#endif
 constexpr int kThreads = 384;          // 3 warpgroups: 2 x epilogue (warps 0-7), 1 x {MMA issuer, producer, 2 idle}
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr int kEpiWarps = 8;
@@ -198,24 +195,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
         // in lock-step both warps contend for the 16-lane XU pipe during the math and leave it idle during this part).
         auto tail = [&](int u0p, int ttp) {
             float p0[4], p1[4], p2[4];
-#if DR_TC_PACKED
-            {   // the same 48 FMAs as below, two per instruction
-                f2 a0 = mk2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0, a2 = a0, b2 = a0;
-#pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const float4 c0 = *reinterpret_cast<const float4*>(cs + u0p + j4);
-                    const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0p + j4);
-                    const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0p + j4);
-                    const f2 hx = mk2(hn[j4], hn[j4 + 1]), hy = mk2(hn[j4 + 2], hn[j4 + 3]);
-                    a0 = fma2(mk2(c0.x, c0.y), hx, a0); b0 = fma2(mk2(c0.z, c0.w), hy, b0);
-                    a1 = fma2(mk2(c1.x, c1.y), hx, a1); b1 = fma2(mk2(c1.z, c1.w), hy, b1);
-                    a2 = fma2(mk2(c2.x, c2.y), hx, a2); b2 = fma2(mk2(c2.z, c2.w), hy, b2);
-                }
-                un2(a0, p0[0], p0[1]); un2(b0, p0[2], p0[3]);
-                un2(a1, p1[0], p1[1]); un2(b1, p1[2], p1[3]);
-                un2(a2, p2[0], p2[1]); un2(b2, p2[2], p2[3]);
-            }
-#else
 #pragma unroll
             for (int i = 0; i < 4; ++i) { p0[i] = 0.f; p1[i] = 0.f; p2[i] = 0.f; }
 #pragma unroll
@@ -227,7 +206,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                 p1[0] = fmaf(c1.x, hn[j4], p1[0]); p1[1] = fmaf(c1.y, hn[j4 + 1], p1[1]); p1[2] = fmaf(c1.z, hn[j4 + 2], p1[2]); p1[3] = fmaf(c1.w, hn[j4 + 3], p1[3]);
                 p2[0] = fmaf(c2.x, hn[j4], p2[0]); p2[1] = fmaf(c2.y, hn[j4 + 1], p2[1]); p2[2] = fmaf(c2.z, hn[j4 + 2], p2[2]); p2[3] = fmaf(c2.w, hn[j4 + 3], p2[3]);
             }
-#endif
             o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
             o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
             o2 += (p2[0] + p2[1]) + (p2[2] + p2[3]);
@@ -304,62 +282,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         cz[4 * v] = b4.x; cz[4 * v + 1] = b4.y; cz[4 * v + 2] = b4.z; cz[4 * v + 3] = b4.w;
                         cn[4 * v] = c.x; cn[4 * v + 1] = c.y; cn[4 * v + 2] = c.z; cn[4 * v + 3] = c.w;
                     }
-#if DR_TC_PACKED
-                    // Same arithmetic, operation for operation and rounding for rounding, as the scalar form below, with every
-                    // fp32 add / mul / fma issued for TWO cells at once (FFMA2 / FMUL2 / FADD2): the epilogue warps are issue
-                    // bound (clock64 r01: 5.7k of the 8.9k cycles of a step are gate math), not FMA-pipe bound.
-                    float zz[8], rv[8], nv[8], pnp[8];
-                    {
-                        const f2 nl2 = mk2(-kLog2e, -kLog2e), one2 = mk2(1.0f, 1.0f), tl2 = mk2(2.0f * kLog2e, 2.0f * kLog2e);
-#pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            float e0, e1, z0, z1;
-                            un2(fma2(mk2(__uint_as_float(gr[j8 + i]), __uint_as_float(gr[j8 + i + 1])), nl2, mk2(cr[i], cr[i + 1])), e0, e1);
-                            un2(fma2(mk2(__uint_as_float(gz[j8 + i]), __uint_as_float(gz[j8 + i + 1])), nl2, mk2(cz[i], cz[i + 1])), z0, z1);
-                            e0 = ex2_approx(fminf(e0, 30.0f)); e1 = ex2_approx(fminf(e1, 30.0f));
-                            z0 = ex2_approx(fminf(z0, 30.0f)); z1 = ex2_approx(fminf(z1, 30.0f));
-                            const f2 er2 = add2(mk2(e0, e1), one2), ez2 = add2(mk2(z0, z1), one2);
-                            float r0, r1;
-                            un2(mul2(er2, ez2), r0, r1);
-                            const float iv = rcp_approx(r0 * r1);              // 1/((1+er0)(1+ez0)(1+er1)(1+ez1))
-                            const f2 inv2 = mul2(mk2(r1, r0), mk2(iv, iv));    // 1/((1+er_i)(1+ez_i)) for both cells
-                            const f2 zz2 = mul2(er2, inv2), rv2 = mul2(ez2, inv2);
-                            un2(zz2, zz[i], zz[i + 1]);
-                            un2(rv2, rv[i], rv[i + 1]);
-                            float t0, t1;
-                            un2(fma2(fma2(rv2, mk2(__uint_as_float(gh[j8 + i]), __uint_as_float(gh[j8 + i + 1])),
-                                          mk2(__uint_as_float(gi[j8 + i]), __uint_as_float(gi[j8 + i + 1]))), tl2, mk2(cn[i], cn[i + 1])), t0, t1);
-                            t0 = ex2_approx(fminf(t0, 30.0f)); t1 = ex2_approx(fminf(t1, 30.0f));
-                            un2(add2(mk2(t0, t1), one2), pnp[i], pnp[i + 1]);
-                        }
-                        float ivn[4];                                         // 1/(pn[2i]*pn[2i+1]) from ONE reciprocal per four cells
-#pragma unroll
-                        for (int g4 = 0; g4 < 2; ++g4) {
-                            const float pa = pnp[4 * g4] * pnp[4 * g4 + 1], pb = pnp[4 * g4 + 2] * pnp[4 * g4 + 3];
-                            const float inv4 = rcp_approx(pa * pb);
-                            ivn[2 * g4] = pb * inv4;
-                            ivn[2 * g4 + 1] = pa * inv4;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            const int j = j8 + i;
-                            const float m2 = -2.0f * ivn[i >> 1];               // exact scaling: fma(pn, -2*ivn, 1) == fma(-2*pn, ivn, 1)
-                            const f2 n2 = fma2(mk2(pnp[i + 1], pnp[i]), mk2(m2, m2), one2);
-                            // h' = (1-z)*n + z*h, evaluated as torch's CPU cell does: (h - n)*z + n  (three roundings, not fused)
-                            const f2 a2 = add2(mul2(sub2(mk2(hreg[q][j], hreg[q][j + 1]), n2), mk2(zz[i], zz[i + 1])), n2);
-                            float a0, a1;
-                            un2(a2, a0, a1);
-                            un2(n2, nv[i], nv[i + 1]);
-                            hreg[q][j] = a0; hreg[q][j + 1] = a1;
-                            hn[j] = a0; hn[j + 1] = a1;
-                            __half2 hi2 = __floats2half2_rn(a0, a1);
-                            float2 back = __half22float2(hi2);
-                            __half2 lo2 = __floats2half2_rn(a0 - back.x, a1 - back.y);
-                            phi[j >> 1] = *reinterpret_cast<uint32_t*>(&hi2);
-                            plo[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
-                        }
-                    }
-#else
                     float er[8], ez[8], rr[8], zz[8], pn[8];
                     // r, z = sigmoid(.): exp via ex2, and ONE reciprocal per two cells: 1/((1+er0)(1+ez0)(1+er1)(1+ez1)).
                     // Arguments are clamped at 2^30 so that four factors cannot overflow (sigmoid error < 1e-9 there).
@@ -417,7 +339,6 @@ dr_gru_tc_kernel(const uint8_t* __restrict__ wtc,     // [M_loc][2 dir][2 cta][k
                         phi[j >> 1] = *reinterpret_cast<uint32_t*>(&hi2);
                         plo[j >> 1] = *reinterpret_cast<uint32_t*>(&lo2);
                     }
-#endif
                     if (kTrain && live) {
                         float* ph = tr.hs + trow * DR_H + u0 + j8;
                         // (column c, this window): row-major  trow*ncols + c   |   lane-major  block + ((c/4)*B + b)*4

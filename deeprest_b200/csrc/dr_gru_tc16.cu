@@ -146,22 +146,15 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_tc16_kernel(Fwd16Args a) {
             float rt[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) rt[j] = ((kb >> j) & 1u) ? hn[j] * a.drop.inv_keep : 0.0f;
-            float p0[4], p1[4], p2[4];
-            {
-                f2 a0 = mk2(0.f, 0.f), b0 = a0, a1 = a0, b1 = a0, a2 = a0, b2 = a0;
+            float p0[4] = {0.f, 0.f, 0.f, 0.f}, p1[4] = {0.f, 0.f, 0.f, 0.f}, p2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int j4 = 0; j4 < 16; j4 += 4) {
-                    const float4 c0 = *reinterpret_cast<const float4*>(cs + u0p + j4);
-                    const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0p + j4);
-                    const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0p + j4);
-                    const f2 hx = mk2(rt[j4], rt[j4 + 1]), hy = mk2(rt[j4 + 2], rt[j4 + 3]);
-                    a0 = fma2(mk2(c0.x, c0.y), hx, a0); b0 = fma2(mk2(c0.z, c0.w), hy, b0);
-                    a1 = fma2(mk2(c1.x, c1.y), hx, a1); b1 = fma2(mk2(c1.z, c1.w), hy, b1);
-                    a2 = fma2(mk2(c2.x, c2.y), hx, a2); b2 = fma2(mk2(c2.z, c2.w), hy, b2);
-                }
-                un2(a0, p0[0], p0[1]); un2(b0, p0[2], p0[3]);
-                un2(a1, p1[0], p1[1]); un2(b1, p1[2], p1[3]);
-                un2(a2, p2[0], p2[1]); un2(b2, p2[2], p2[3]);
+            for (int j4 = 0; j4 < 16; j4 += 4) {
+                const float4 c0 = *reinterpret_cast<const float4*>(cs + u0p + j4);
+                const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u0p + j4);
+                const float4 c2 = *reinterpret_cast<const float4*>(cs + 2 * DR_H + u0p + j4);
+                p0[0] = fmaf(c0.x, rt[j4], p0[0]); p0[1] = fmaf(c0.y, rt[j4 + 1], p0[1]); p0[2] = fmaf(c0.z, rt[j4 + 2], p0[2]); p0[3] = fmaf(c0.w, rt[j4 + 3], p0[3]);
+                p1[0] = fmaf(c1.x, rt[j4], p1[0]); p1[1] = fmaf(c1.y, rt[j4 + 1], p1[1]); p1[2] = fmaf(c1.z, rt[j4 + 2], p1[2]); p1[3] = fmaf(c1.w, rt[j4 + 3], p1[3]);
+                p2[0] = fmaf(c2.x, rt[j4], p2[0]); p2[1] = fmaf(c2.y, rt[j4 + 1], p2[1]); p2[2] = fmaf(c2.z, rt[j4 + 2], p2[2]); p2[3] = fmaf(c2.w, rt[j4 + 3], p2[3]);
             }
             o0 += (p0[0] + p0[1]) + (p0[2] + p0[3]);
             o1 += (p1[0] + p1[1]) + (p1[2] + p1[3]);
@@ -230,52 +223,50 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_tc16_kernel(Fwd16Args a) {
                         cz[4 * v] = b4.x; cz[4 * v + 1] = b4.y; cz[4 * v + 2] = b4.z; cz[4 * v + 3] = b4.w;
                         cn[4 * v] = c.x; cn[4 * v + 1] = c.y; cn[4 * v + 2] = c.z; cn[4 * v + 3] = c.w;
                     }
-                    // gate math with packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2), as in dr_gru_tc.cu
-                    float zz[8], rv[8], nv[8], pnp[8];
-                    {
-                        const f2 nl2 = mk2(-kLog2e, -kLog2e), one2 = mk2(1.0f, 1.0f), tl2 = mk2(2.0f * kLog2e, 2.0f * kLog2e);
+                    float er[8], ez[8], rr[8], zz[8], en[8], rv[8], nv[8];
 #pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            float e0, e1, z0, z1;
-                            un2(fma2(mk2(__uint_as_float(gr[j8 + i]), __uint_as_float(gr[j8 + i + 1])), nl2, mk2(cr[i], cr[i + 1])), e0, e1);
-                            un2(fma2(mk2(__uint_as_float(gz[j8 + i]), __uint_as_float(gz[j8 + i + 1])), nl2, mk2(cz[i], cz[i + 1])), z0, z1);
-                            e0 = ex2_approx(fminf(e0, 30.0f)); e1 = ex2_approx(fminf(e1, 30.0f));
-                            z0 = ex2_approx(fminf(z0, 30.0f)); z1 = ex2_approx(fminf(z1, 30.0f));
-                            const f2 er2 = add2(mk2(e0, e1), one2), ez2 = add2(mk2(z0, z1), one2);
-                            float r0, r1;
-                            un2(mul2(er2, ez2), r0, r1);
-                            const float iv = rcp_approx(r0 * r1);
-                            const f2 inv2 = mul2(mk2(r1, r0), mk2(iv, iv));
-                            const f2 zz2 = mul2(er2, inv2), rv2 = mul2(ez2, inv2);
-                            un2(zz2, zz[i], zz[i + 1]);
-                            un2(rv2, rv[i], rv[i + 1]);
-                            float t0, t1;
-                            un2(fma2(fma2(rv2, mk2(__uint_as_float(gh[j8 + i]), __uint_as_float(gh[j8 + i + 1])),
-                                          mk2(__uint_as_float(gi[j8 + i]), __uint_as_float(gi[j8 + i + 1]))), tl2, mk2(cn[i], cn[i + 1])), t0, t1);
-                            t0 = ex2_approx(fminf(t0, 30.0f)); t1 = ex2_approx(fminf(t1, 30.0f));
-                            un2(add2(mk2(t0, t1), one2), pnp[i], pnp[i + 1]);
-                        }
-                        float ivn[4];
+                    for (int i = 0; i < 8; ++i) {
+                        er[i] = fminf(fmaf(__uint_as_float(gr[j8 + i]), -kLog2e, cr[i]), 30.0f);
+                        ez[i] = fminf(fmaf(__uint_as_float(gz[j8 + i]), -kLog2e, cz[i]), 30.0f);
+                    }
 #pragma unroll
-                        for (int g4 = 0; g4 < 2; ++g4) {
-                            const float pa = pnp[4 * g4] * pnp[4 * g4 + 1], pb = pnp[4 * g4 + 2] * pnp[4 * g4 + 3];
-                            const float inv4 = rcp_approx(pa * pb);
-                            ivn[2 * g4] = pb * inv4;
-                            ivn[2 * g4 + 1] = pa * inv4;
-                        }
+                    for (int i = 0; i < 8; ++i) { er[i] = ex2_approx(er[i]); ez[i] = ex2_approx(ez[i]); }
 #pragma unroll
-                        for (int i = 0; i < 8; i += 2) {
-                            const int j = j8 + i;
-                            const float m2 = -2.0f * ivn[i >> 1];
-                            const f2 n2 = fma2(mk2(pnp[i + 1], pnp[i]), mk2(m2, m2), one2);
-                            const f2 a2 = add2(mul2(sub2(mk2(hreg[q][j], hreg[q][j + 1]), n2), mk2(zz[i], zz[i + 1])), n2);
-                            float a0, a1;
-                            un2(a2, a0, a1);
-                            un2(n2, nv[i], nv[i + 1]);
-                            hreg[q][j] = a0; hreg[q][j + 1] = a1;
-                            hn[j] = a0; hn[j + 1] = a1;
-                            ph[j >> 1] = pack_bf2(a0, a1);
-                        }
+                    for (int i = 0; i < 8; ++i) { er[i] += 1.0f; ez[i] += 1.0f; rr[i] = er[i] * ez[i]; }
+                    float iv2[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) iv2[i] = rcp_approx(rr[2 * i] * rr[2 * i + 1]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float inv = rr[i ^ 1] * iv2[i >> 1];          // 1/((1+er_i)(1+ez_i))
+                        zz[i] = er[i] * inv;
+                        rv[i] = ez[i] * inv;
+                        const float t = fmaf(rv[i], __uint_as_float(gh[j8 + i]), __uint_as_float(gi[j8 + i]));
+                        en[i] = fminf(fmaf(t, 2.0f * kLog2e, cn[i]), 30.0f);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) en[i] = ex2_approx(en[i]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) en[i] += 1.0f;
+                    float ivn[4];
+#pragma unroll
+                    for (int g4 = 0; g4 < 2; ++g4) {
+                        const float pa = en[4 * g4] * en[4 * g4 + 1], pb = en[4 * g4 + 2] * en[4 * g4 + 3];
+                        const float inv4 = rcp_approx(pa * pb);
+                        ivn[2 * g4] = pb * inv4;
+                        ivn[2 * g4 + 1] = pa * inv4;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const int j = j8 + i;
+                        const float n0 = fmaf(-2.0f * en[i + 1], ivn[i >> 1], 1.0f);
+                        const float n1 = fmaf(-2.0f * en[i], ivn[i >> 1], 1.0f);
+                        const float a0 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j], n0), zz[i]), n0);
+                        const float a1 = __fadd_rn(__fmul_rn(__fsub_rn(hreg[q][j + 1], n1), zz[i + 1]), n1);
+                        hreg[q][j] = a0; hreg[q][j + 1] = a1;
+                        hn[j] = a0; hn[j + 1] = a1;
+                        nv[i] = n0; nv[i + 1] = n1;
+                        ph[j >> 1] = pack_bf2(a0, a1);
                     }
 #pragma unroll
                     for (int i = 0; i < 8; i += 2) {

@@ -41,10 +41,6 @@ __device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
     return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
 
-using drtc::f2; using drtc::mk2; using drtc::un2; using drtc::fma2; using drtc::mul2; using drtc::add2; using drtc::sub2;
-__device__ __forceinline__ f2 unpack_bf2p(uint32_t u) { return mk2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u)); }
-__device__ __forceinline__ uint32_t pack_bf2p(f2 a) { float x, y; un2(a, x, y); return pack_bf2(x, y); }
-
 // ---- dropout keep decisions (qrnn.py:43): replayed uint8 mask (parity tests) or a counter-based draw ----
 // One 64-bit hash serves 4 consecutive elements (16 bits each): element idx keeps iff lane(idx & 3) of hash(idx >> 2) >= thr16,
 // thr16 = round(p * 65536).  Identical in the forward (r~ = keep * h), the backward (adjoint) and the head-gradient kernels.
