@@ -451,7 +451,7 @@ def shared_host_tensor(shape, rank, world, tag):
         dist.broadcast(ok, 0)
     if float(ok.item()) < 1:
         t = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
-        return t.numpy(), True, False
+        return t.numpy(), True, False, (lambda: None)
     arr = np.memmap(path, dtype=np.float32, mode="r+", shape=tuple(shape))
     rt = torch.cuda.cudart()
     rc = rt.cudaHostRegister(arr.ctypes.data, n, 0)
@@ -460,7 +460,13 @@ def shared_host_tensor(shape, rank, world, tag):
         dist.barrier()
     if rank == 0:
         os.unlink(path)                                        # the mappings keep it alive
-    return arr, pinned, True
+
+    def release():
+        # the registration must be dropped BEFORE the mapping goes away: a munmap'ed but still registered range stays in the
+        # CUDA address space and a later large cudaMalloc that lands on it fails with cudaErrorAlreadyMapped
+        if pinned:
+            rt.cudaHostUnregister(arr.ctypes.data)
+    return arr, pinned, True, release
 
 
 def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
@@ -546,9 +552,9 @@ def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
     x_np = x_host.numpy()
     if world == 1:
         out_host = torch.empty((B, T, M, layout.Q), dtype=torch.float32, pin_memory=True)
-        out_np, pinned, shared = out_host.numpy(), True, False
+        out_np, pinned, shared, release_host = out_host.numpy(), True, False, (lambda: None)
     else:
-        out_np, pinned, shared = shared_host_tensor((B, T, M, layout.Q), rank, world, tag)
+        out_np, pinned, shared, release_host = shared_host_tensor((B, T, M, layout.Q), rank, world, tag)
     d2h = B * T * M_loc * layout.Q * 4
 
     def e2e_step():
@@ -594,9 +600,12 @@ def measure_inference(args, rank, world, dev, S, B, T, F, peaks, tag):
     final = out.detach().cpu().numpy() if rank == 0 else None
     e2e_final = np.array(out_np[:4]) if rank == 0 else None
     model.close()
+    torch.cuda.synchronize()
+    release_host()
+    del out_np
     del x_dev
     torch.cuda.empty_cache()
-    barrier()                                  # every rank has unmapped this model's arenas before anyone allocates the next
+    barrier()
     return res, final, e2e_final, x_host
 
 
@@ -643,8 +652,7 @@ def run_ours(args, rank, world, local_rank):
     peaks = measured_peaks()
 
     blk4 = None
-    # (runs FIRST: its tens-of-GB activation images must be allocated before this process maps any peer memory through CUDA
-    #  IPC — afterwards cudaMalloc of that size fails with "resource already mapped" on this driver)
+    # (runs first: it needs the most device memory, before the inference models and their exchange arenas exist)
     # ---- BASELINE configs[4]: long-horizon bf16 training, experts sharded over the GPUs ----
     if world > 1 and (world == 8 or args.configs4) and not args.no_configs4:
         try:

@@ -25,11 +25,11 @@ namespace {
 constexpr int kMaxWorld = 8, kMaxChunks = 64, kChunk = 256, kRing = 256;
 typedef CUresult (*PFN_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
-// One arena per device and process, kept until the process exits.  On this driver (580.x) a large cudaMalloc issued after a
-// CUDA-IPC mapping has been opened AND closed in the same process fails with cudaErrorAlreadyMapped, so arenas and peer
-// mappings are never released: a later model on the same device (e.g. a second, larger estimator) reuses the arena if it
-// fits — create the model with the largest [Bmax, T, M] first, or set DR_COMM_ARENA_GB.  Epochs are per arena, so flags left
-// by an earlier model are always older than any new forward's.
+// One arena per device and process, kept until the process exits: a later model on the same device (e.g. a second estimator
+// with more experts) reuses the arena and the peer mappings instead of exchanging IPC handles again, and an exported
+// allocation is never freed while an importer may still map it (the CUDA IPC teardown rule).  The arena must fit the largest
+// model: create that one first, or set DR_COMM_ARENA_GB.  Epochs are per arena, so flags left by an earlier model are always
+// older than any new forward's.
 struct GlobalArena {
     uint8_t* base; size_t bytes;
     uint8_t* peer[kMaxWorld]; bool ipc_open[kMaxWorld]; bool have_peers;
