@@ -89,12 +89,4 @@ __device__ __forceinline__ uint32_t keep4(const Drop& d, size_t idx) {
     for (int j = 0; j < 4; ++j) bits |= (((uint32_t)(h >> (16 * j)) & 0xFFFFu) >= d.thr16 ? 1u : 0u) << j;
     return bits;
 }
-// same for a single element
-__device__ __forceinline__ bool keep1(const Drop& d, size_t idx) {
-    if (d.mask) return d.mask[idx] != 0;
-    if (d.thr16 == 0) return true;
-    const uint64_t h = mix64(d.seed * 0x9E3779B97F4A7C15ull + (uint64_t)(idx >> 2));
-    return ((uint32_t)(h >> (16 * (idx & 3))) & 0xFFFFu) >= d.thr16;
-}
-
 }  // namespace drt16
