@@ -8,6 +8,8 @@
 //   * (r, z, n, q) read from the gate image and (da_r, da_z, da_n, dq) written back IN PLACE, already in the operand
 //     layout the weight-gradient GEMMs bulk-copy.
 // Work item = (128-window tile, expert, direction), one CTA, thread = window (TMEM lane), warp / 4 = hidden half.
+#include <cstdio>
+#include <cstdlib>
 #include "dr_t16.cuh"
 
 using namespace drtc;
@@ -30,11 +32,12 @@ struct Bwd16Args {
     const uint8_t* wimg;      // [M_loc][2][kWImg]
     uint8_t* gate;            // gate images, in: (r,z,n,q)  out: (da_r,da_z,da_n,dq)
     const uint8_t* himg;      // h images
-    const float* dy;          // dL/dy of the micro-batch [Bm][T][M_loc][Q]
-    const float* gbar;        // [Bm*T][2H]  row = b*T + t
+    const float* dy;          // dL/dy of the micro-batch, TIME-major [T][Bm][M_loc][Q]
+    const float* gbar;        // [T*Bm][2H]  row = t*Bm + b (time-major: the 128 windows of a tile and step are contiguous)
     const float* ct;          // [M_loc][2][Q][H]
     Drop drop;
     int B, T, M_loc, ntiles, e_lo, b0, Bfull;
+    unsigned long long* dbg;   // nullable: clock64 breakdown of work item 0 (DR_BWD16_DBG=1, measurement hook)
 };
 
 __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) {
@@ -78,51 +81,53 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
 #pragma unroll
         for (int j = 0; j < 64; ++j) dh[j] = 0.0f;
         uint32_t d_phase = 0;
+        const bool timing = a.dbg != nullptr && item == 0 && warp == 0 && lane == 0;
+        long long t_work = 0, t_wait = 0, t_dread = 0, t_ld = 0, t_gb = 0, t_math = 0, t_st = 0;
+        const long long t_begin = clock64();
         for (int s = T - 1; s >= 0; --s) {                      // reverse of the forward processing order
+            const long long ts0 = timing ? clock64() : 0;
             const int t = dir ? (T - 1 - s) : s;
             const int tp = dir ? t + 1 : t - 1;                 // the step whose output was this step's h_prev
             uint8_t* gimg = a.gate + blk_index(dir, e, t, tile, a.M_loc, T, a.ntiles) * kGateImg + (size_t)half * kColBlk;
             const uint8_t* hpim = a.himg + blk_index(dir, e, s > 0 ? tp : t, tile, a.M_loc, T, a.ntiles) * kHImg + (size_t)half * kColBlk;
-            const float* gb = a.gbar + (bb * T + t) * DR_2H + dir * DR_H + half * 64;
+            const float* gb = a.gbar + ((size_t)t * B + bb) * DR_2H + dir * DR_H + half * 64;
             float d0 = 0.f, d1 = 0.f, d2 = 0.f;
             if (live) {
-                const float* dd = a.dy + ((bb * T + t) * a.M_loc + e) * DR_Q;
+                const float* dd = a.dy + (((size_t)t * B + bb) * a.M_loc + e) * DR_Q;
                 d0 = dd[0]; d1 = dd[1]; d2 = dd[2];
-            }
-            if (s > 0) {                                        // next iteration's rows (step tp): warm L2 while this step runs
-                const long long nb = (long long)(dir ? 1 : -1) * (long long)a.ntiles;
-                const uint32_t ro = img_off(row, 0) & ~127u;                     // this window's 128-byte row
-                const uint8_t* gnext = gimg + nb * (long long)kGateImg + ro;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) prefetch_l2(gnext + (size_t)g * 2 * kColBlk);
-                if (s > 1) prefetch_l2(hpim + nb * (long long)kHImg + ro);
-                if (live) { prefetch_l2(gb + (long long)(dir ? 1 : -1) * DR_2H); prefetch_l2(gb + (long long)(dir ? 1 : -1) * DR_2H + 32); }
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                       // 16 hidden units at a time = two 16-byte chunks per array
-                const uint32_t o0 = img_off(row, 2 * c), o1 = img_off(row, 2 * c + 1);
+                const long long tg0 = timing ? clock64() : 0;
                 uint32_t wr[8], wz[8], wn[8], wq[8], wh[8];
-                {
-                    const uint4 r0 = *reinterpret_cast<const uint4*>(gimg + o0), r1 = *reinterpret_cast<const uint4*>(gimg + o1);
-                    const uint4 z0 = *reinterpret_cast<const uint4*>(gimg + 2 * kColBlk + o0), z1 = *reinterpret_cast<const uint4*>(gimg + 2 * kColBlk + o1);
-                    const uint4 n0 = *reinterpret_cast<const uint4*>(gimg + 4 * kColBlk + o0), n1 = *reinterpret_cast<const uint4*>(gimg + 4 * kColBlk + o1);
-                    const uint4 q0 = *reinterpret_cast<const uint4*>(gimg + 6 * kColBlk + o0), q1 = *reinterpret_cast<const uint4*>(gimg + 6 * kColBlk + o1);
-                    uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
-                    if (s > 0) { h0 = __ldg(reinterpret_cast<const uint4*>(hpim + o0)); h1 = __ldg(reinterpret_cast<const uint4*>(hpim + o1)); }
-                    wr[0] = r0.x; wr[1] = r0.y; wr[2] = r0.z; wr[3] = r0.w; wr[4] = r1.x; wr[5] = r1.y; wr[6] = r1.z; wr[7] = r1.w;
-                    wz[0] = z0.x; wz[1] = z0.y; wz[2] = z0.z; wz[3] = z0.w; wz[4] = z1.x; wz[5] = z1.y; wz[6] = z1.z; wz[7] = z1.w;
-                    wn[0] = n0.x; wn[1] = n0.y; wn[2] = n0.z; wn[3] = n0.w; wn[4] = n1.x; wn[5] = n1.y; wn[6] = n1.z; wn[7] = n1.w;
-                    wq[0] = q0.x; wq[1] = q0.y; wq[2] = q0.z; wq[3] = q0.w; wq[4] = q1.x; wq[5] = q1.y; wq[6] = q1.z; wq[7] = q1.w;
-                    wh[0] = h0.x; wh[1] = h0.y; wh[2] = h0.z; wh[3] = h0.w; wh[4] = h1.x; wh[5] = h1.y; wh[6] = h1.z; wh[7] = h1.w;
+                ld_cols16(gimg, row, c, wr);                              // one 256-bit load per array: both halves of the sector
+                ld_cols16(gimg + 2 * kColBlk, row, c, wz);
+                ld_cols16(gimg + 4 * kColBlk, row, c, wn);
+                ld_cols16(gimg + 6 * kColBlk, row, c, wq);
+                if (s > 0) ld_cols16(hpim, row, c, wh);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) wh[i] = 0u;
                 }
+                uint32_t gw[16];                                          // G-bar of these 16 units: issued with the image loads (one wait)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) gw[i] = 0u;
+                if (live) {
+                    uint32_t g0[8], g1[8];
+                    ld256(gb + c * 16, g0);
+                    ld256(gb + c * 16 + 8, g1);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { gw[i] = g0[i]; gw[8 + i] = g1[i]; }
+                }
+                long long tg1 = 0;
+                if (timing) { asm volatile("" :: "r"(wr[0]), "r"(wz[0]), "r"(wn[0]), "r"(wq[0]), "r"(wh[7])); tg1 = clock64(); }
                 // adjoint arriving from the heads for these 16 units: keep/(1-p) * (Ct^T dy + G-bar)
                 float dv[16];
                 {
                     const uint32_t kb = live ? keep16(a.drop, drop_base + (size_t)t * DR_2H + c * 16) : 0u;
 #pragma unroll
                     for (int v = 0; v < 16; v += 4) {
-                        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) g4 = __ldg(reinterpret_cast<const float4*>(gb + c * 16 + v));
+                        const float4 g4 = make_float4(__uint_as_float(gw[v]), __uint_as_float(gw[v + 1]), __uint_as_float(gw[v + 2]), __uint_as_float(gw[v + 3]));
                         const int u = half * 64 + c * 16 + v;
                         const float4 c0 = *reinterpret_cast<const float4*>(cs + u);
                         const float4 c1 = *reinterpret_cast<const float4*>(cs + DR_H + u);
@@ -137,6 +142,8 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                         dv[v + 3] = ((kb >> (v + 3)) & 1u) ? s3 : 0.0f;
                     }
                 }
+                long long tg2 = 0;
+                if (timing) { asm volatile("" :: "f"(dv[0]), "f"(dv[15])); tg2 = clock64(); }
                 uint32_t par[8], paz[8], pan[8], pdq[8];
 #pragma unroll
                 for (int v = 0; v < 16; v += 2) {               // dr_gate_bwd_kernel's arithmetic on the bf16-stored activations
@@ -163,14 +170,13 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                     pdq[v >> 1] = pack_bf2(out4[0][3], out4[1][3]);
                 }
                 // adjoints back into the gate image, in place (dead rows stay zero: every input of theirs is zero)
-                *reinterpret_cast<uint4*>(gimg + o0) = make_uint4(par[0], par[1], par[2], par[3]);
-                *reinterpret_cast<uint4*>(gimg + o1) = make_uint4(par[4], par[5], par[6], par[7]);
-                *reinterpret_cast<uint4*>(gimg + 2 * kColBlk + o0) = make_uint4(paz[0], paz[1], paz[2], paz[3]);
-                *reinterpret_cast<uint4*>(gimg + 2 * kColBlk + o1) = make_uint4(paz[4], paz[5], paz[6], paz[7]);
-                *reinterpret_cast<uint4*>(gimg + 4 * kColBlk + o0) = make_uint4(pan[0], pan[1], pan[2], pan[3]);
-                *reinterpret_cast<uint4*>(gimg + 4 * kColBlk + o1) = make_uint4(pan[4], pan[5], pan[6], pan[7]);
-                *reinterpret_cast<uint4*>(gimg + 6 * kColBlk + o0) = make_uint4(pdq[0], pdq[1], pdq[2], pdq[3]);
-                *reinterpret_cast<uint4*>(gimg + 6 * kColBlk + o1) = make_uint4(pdq[4], pdq[5], pdq[6], pdq[7]);
+                long long tg3 = 0;
+                if (timing) { asm volatile("" :: "r"(par[0]), "r"(pdq[7])); tg3 = clock64(); }
+                st_cols16(gimg, row, c, par);
+                st_cols16(gimg + 2 * kColBlk, row, c, paz);
+                st_cols16(gimg + 4 * kColBlk, row, c, pan);
+                st_cols16(gimg + 6 * kColBlk, row, c, pdq);
+                if (timing) { const long long tg4 = clock64(); t_ld += tg1 - tg0; t_gb += tg2 - tg1; t_math += tg3 - tg2; t_st += tg4 - tg3; }
                 if (s > 0) {                                    // A operand of this step's product: dgh = (da_r, da_z, dq), k = gate*128 + unit
                     const uint32_t col = (uint32_t)(half * 64 + c * 16) / 2;
                     tmem_st8(tbase + lane_base + kColA + col, par);
@@ -183,9 +189,12 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(BW_A_READY));
+                const long long ts1 = timing ? clock64() : 0;
                 mbar_wait(bar(BW_D_FULL), d_phase);
                 d_phase ^= 1;
                 tc_fence_after();
+                const long long ts2 = timing ? clock64() : 0;
+                if (timing) { t_work += ts1 - ts0; t_wait += ts2 - ts1; }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     uint32_t dd[16];
@@ -195,7 +204,13 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
                     for (int v = 0; v < 16; ++v) dh[c * 16 + v] += __uint_as_float(dd[v]);
                 }
                 tc_fence_before();                              // D is free again once every warp arrives on A_READY
+                if (timing) t_dread += clock64() - ts2;
             }
+        }
+        if (timing) {
+            a.dbg[0] = (unsigned long long)(clock64() - t_begin); a.dbg[1] = (unsigned long long)t_work;
+            a.dbg[2] = (unsigned long long)t_wait; a.dbg[3] = (unsigned long long)t_dread; a.dbg[4] = (unsigned long long)T;
+            a.dbg[5] = (unsigned long long)t_ld; a.dbg[6] = (unsigned long long)t_gb; a.dbg[7] = (unsigned long long)t_math; a.dbg[8] = (unsigned long long)t_st;
         }
     } else {
         // ======================= weight load + MMA issuer (one elected thread of warp 8) =======================
@@ -207,7 +222,25 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_bwd16_kernel(Bwd16Args a) 
             mbar_wait(bar(BW_W_LAND), 0);
             const uint32_t idesc = make_idesc_bf16(128, 128);
             const uint64_t wdesc = make_desc_sw128(smem_u32(smem));
+            // L2 prefetch of the activations two steps ahead, one bulk request per contiguous 16 KB column block (a per-row
+            // `prefetch.global.L2` covers one 32-byte sector: the clock64 breakdown showed every group's loads at DRAM latency)
+            auto prefetch_step = [&](int sp) {
+                if (sp < 0) return;
+                const int tq = dir ? (T - 1 - sp) : sp;
+                const uint8_t* gq = a.gate + blk_index(dir, e, tq, tile, a.M_loc, T, a.ntiles) * kGateImg;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gq), "r"(kGateImg) : "memory");
+                if (sp > 0) {
+                    const int tpq = dir ? tq + 1 : tq - 1;
+                    const uint8_t* hq = a.himg + blk_index(dir, e, tpq, tile, a.M_loc, T, a.ntiles) * kHImg;
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(hq), "r"(kHImg) : "memory");
+                }
+                const int rows = min(128, a.B - tile * 128);
+                const float* gbq = a.gbar + ((size_t)tq * a.B + tile * 128) * DR_2H;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(gbq), "r"((uint32_t)(rows * DR_2H * 4)) : "memory");
+            };
+            prefetch_step(T - 1); prefetch_step(T - 2);
             for (int it = 0; it < T - 1; ++it) {
+                prefetch_step(T - 3 - it);
                 mbar_wait(bar(BW_A_READY), it & 1);
                 tc_fence_after();
 #pragma unroll 1
@@ -271,8 +304,21 @@ int dr_launch_gru_bwd16(dr_model* m, const uint8_t* whT, uint8_t* gate, const ui
     a.drop.mask = mask; a.drop.seed = seed; a.drop.inv_keep = 1.0f / (1.0f - p);
     a.drop.thr16 = (uint32_t)(p * 65536.0f + 0.5f);
     a.B = Bm; a.T = T; a.M_loc = Ml; a.ntiles = (Bm + 127) / 128; a.e_lo = m->e_lo; a.b0 = b0; a.Bfull = Bfull;
+    a.dbg = nullptr;
+    unsigned long long* dbg = nullptr;
+    if (getenv("DR_BWD16_DBG")) { cudaMalloc((void**)&dbg, 128); cudaMemset(dbg, 0, 128); a.dbg = dbg; }
     DR_CUDA(m, cudaFuncSetAttribute(dr_gru_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     dr_gru_bwd16_kernel<<<Ml * 2 * a.ntiles, kThreads, kSmem, m->stream>>>(a);
+    if (dbg) {                                                  // measurement hook: cycles per step of work item 0, warp 0
+        unsigned long long h[16] = {0};
+        cudaStreamSynchronize(m->stream);
+        cudaMemcpy(h, dbg, 128, cudaMemcpyDeviceToHost);
+        cudaFree(dbg);
+        if (h[4]) fprintf(stderr, "[bwd16 timing, item 0 warp 0] cycles per step: total %.0f  loads+math+stores %.0f  wait(MMA + other warps) %.0f  D read %.0f\n",
+                          (double)h[0] / h[4], (double)h[1] / h[4], (double)h[2] / h[4], (double)h[3] / h[4]);
+        if (h[4]) fprintf(stderr, "[bwd16 timing] inside loads+math+stores, per step: image loads until first use %.0f  dy/G-bar adjoint %.0f  gate adjoints %.0f  stores issued %.0f\n",
+                          (double)h[5] / h[4], (double)h[6] / h[4], (double)h[7] / h[4], (double)h[8] / h[4]);
+    }
     DR_CUDA(m, cudaGetLastError());
     m->launches += 1;
     return DR_OK;

@@ -285,21 +285,17 @@ __global__ void __launch_bounds__(kThreads, 1) dr_gru_tc16_kernel(Fwd16Args a) {
                 // saved activations: 16 columns = two 16-byte chunks per gate.  Rows past the batch are written as zeros: the
                 // weight-gradient GEMMs read whole 64-window chunks.
                 {
-                    const int cb = u0 >> 6, ch = (u0 & 63) >> 3;
-                    const uint32_t o0b = img_off(row, ch), o1b = img_off(row, ch + 1);
-                    const uint4 zero = make_uint4(0, 0, 0, 0);
+                    const int cb = u0 >> 6, sc = (u0 & 63) >> 4;           // column block, 32-byte sector of the row (16 columns)
+                    if (!live) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { pr[i] = 0u; pz[i] = 0u; pn[i] = 0u; pq[i] = 0u; ph[i] = 0u; }
+                    }
                     uint8_t* g0 = gimg + (size_t)cb * kColBlk;
-                    *reinterpret_cast<uint4*>(g0 + o0b) = live ? make_uint4(pr[0], pr[1], pr[2], pr[3]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + o1b) = live ? make_uint4(pr[4], pr[5], pr[6], pr[7]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 2 * kColBlk + o0b) = live ? make_uint4(pz[0], pz[1], pz[2], pz[3]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 2 * kColBlk + o1b) = live ? make_uint4(pz[4], pz[5], pz[6], pz[7]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 4 * kColBlk + o0b) = live ? make_uint4(pn[0], pn[1], pn[2], pn[3]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 4 * kColBlk + o1b) = live ? make_uint4(pn[4], pn[5], pn[6], pn[7]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 6 * kColBlk + o0b) = live ? make_uint4(pq[0], pq[1], pq[2], pq[3]) : zero;
-                    *reinterpret_cast<uint4*>(g0 + 6 * kColBlk + o1b) = live ? make_uint4(pq[4], pq[5], pq[6], pq[7]) : zero;
-                    uint8_t* h0 = himg + (size_t)cb * kColBlk;
-                    *reinterpret_cast<uint4*>(h0 + o0b) = live ? make_uint4(ph[0], ph[1], ph[2], ph[3]) : zero;
-                    *reinterpret_cast<uint4*>(h0 + o1b) = live ? make_uint4(ph[4], ph[5], ph[6], ph[7]) : zero;
+                    st_cols16(g0, row, sc, pr);                            // one 256-bit store per array (see dr_t16.cuh)
+                    st_cols16(g0 + 2 * kColBlk, row, sc, pz);
+                    st_cols16(g0 + 4 * kColBlk, row, sc, pn);
+                    st_cols16(g0 + 6 * kColBlk, row, sc, pq);
+                    st_cols16(himg + (size_t)cb * kColBlk, row, sc, ph);
                 }
                 if (half == 0) { tail(u0, tt); if (q == 3) flush(tt); }
             }

@@ -41,6 +41,40 @@ __device__ __forceinline__ float2 unpack_bf2(uint32_t u) {
     return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
 }
 
+// ---- 32-byte sector access to a thread's image row ----
+// A thread of the recurrence kernels touches its window's 128-byte row 16 columns (two 16-byte chunks 2c, 2c+1) at a time.
+// The two chunks are the halves of ONE aligned 32-byte sector (the swizzle flips only their order, by the row's parity), so
+// they move with a single 256-bit load / store (LDG.256 / STG.256, sm_100).  This matters: with one row per lane every warp
+// instruction touches 32 different cache lines, and the clock64 breakdown of the reverse chain (profiles/r02_bwd16_lsu.md)
+// showed the kernel bound by exactly that — 22.7k of 25.9k cycles per step in loads + stores at one line per cycle.
+__device__ __forceinline__ void ld256(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st256(void* p, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+// byte offset of the sector holding chunks 2c and 2c+1 of window `row` inside a column block
+__host__ __device__ inline uint32_t sector_off(int row, int c) {
+    return (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((((2 * c) ^ (row & 7)) & ~1) << 4);
+}
+// v[0..7] = the 16 consecutive bf16 columns 16c .. 16c+15 of the row (as 8 pairs), in column order
+__device__ __forceinline__ void ld_cols16(const uint8_t* colblk, int row, int c, uint32_t (&v)[8]) {
+    uint32_t w[8];
+    ld256(colblk + sector_off(row, c), w);
+    const bool flip = row & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = flip ? w[4 + i] : w[i]; v[4 + i] = flip ? w[i] : w[4 + i]; }
+}
+__device__ __forceinline__ void st_cols16(uint8_t* colblk, int row, int c, const uint32_t (&v)[8]) {
+    uint32_t w[8];
+    const bool flip = row & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[i] = flip ? v[4 + i] : v[i]; w[4 + i] = flip ? v[i] : v[4 + i]; }
+    st256(colblk + sector_off(row, c), w);
+}
+
 // ---- dropout keep decisions (qrnn.py:43): replayed uint8 mask (parity tests) or a counter-based draw ----
 // One 64-bit hash serves 4 consecutive elements (16 bits each): element idx keeps iff lane(idx & 3) of hash(idx >> 2) >= thr16,
 // thr16 = round(p * 65536).  Identical in the forward (r~ = keep * h), the backward (adjoint) and the head-gradient kernels.

@@ -229,18 +229,27 @@ __global__ void dr_head_fwd_kernel(const float* __restrict__ hs0, const float* _
 }
 
 // dL/dout (qrnn.py:58-67 through torch.max's tie rule) and the loss partial sum
+// tm_B > 0: dy is written TIME-major, dy[(t*tm_B + b)][M_loc][Q] (bf16 engine: the windows of a step are contiguous for the
+// backward kernels); out / y stay in the reference's [b][t][m] order.
 __global__ void dr_loss_grad_kernel(const float* __restrict__ out, const float* __restrict__ y, float* __restrict__ dy,
-                                    size_t n_rm, float q0, float q1, float q2, float inv_n, double* acc) {
+                                    size_t n_rm, float q0, float q1, float q2, float inv_n, double* acc,
+                                    int tm_B = 0, int tm_T = 0, int tm_M = 0) {
     float local = 0.0f;
     const float qs[3] = {q0, q1, q2};
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rm; i += (size_t)gridDim.x * blockDim.x) {
         float yy = y[i];
+        size_t o = i;
+        if (tm_B > 0) {
+            const size_t e_ = i % tm_M, bt = i / tm_M;
+            const size_t t_ = bt % tm_T, b_ = bt / tm_T;
+            o = (t_ * tm_B + b_) * tm_M + e_;
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             float e = yy - out[i * DR_Q + k];
             local += fmaxf((qs[k] - 1.0f) * e, qs[k] * e);
             float g = (e < 0.0f) ? (1.0f - qs[k]) : (e > 0.0f) ? -qs[k] : (0.5f - qs[k]);
-            dy[i * DR_Q + k] = g * inv_n;
+            dy[o * DR_Q + k] = g * inv_n;
         }
     }
     __shared__ double red[256];
@@ -447,14 +456,14 @@ __global__ void __launch_bounds__(256) dr_head_grad16_kernel(const uint8_t* __re
         for (int i = 0; i < 4; ++i) { u[q][i] = 0.f; v[q][i] = 0.f; }
     const size_t col_off = (size_t)(j0 >> 6) * drt16::kColBlk + (size_t)(j0 & 7) * 2;
     const int chunk = (j0 & 63) >> 3;
-    const size_t dy_bstride = (size_t)T * M_loc * DR_Q;
+    const size_t dy_bstride = (size_t)M_loc * DR_Q;
     const size_t drop_bstride = (size_t)T * DR_2H;
     for (int t = t0; t < t1; ++t) {
         for (int tile = 0; tile < ntiles; ++tile) {
             const uint8_t* hblk = himg + drt16::blk_index(d, e, t, tile, M_loc, T, ntiles) * drt16::kHImg + col_off;
             const float* sblk = S + (((size_t)t * 64 + kg) * Bp + tile * 128) * 4;
             const int nb = min(128, Bm - tile * 128);
-            const float* dblk = dy + ((size_t)(tile * 128) * T + t) * M_loc * DR_Q + (size_t)e * DR_Q;
+            const float* dblk = dy + ((size_t)t * Bm + tile * 128) * M_loc * DR_Q + (size_t)e * DR_Q;     // dy is time-major
             const size_t dbase = (((size_t)(e_lo + e) * Bfull + b0 + tile * 128) * T + t) * DR_2H + k0;
 #pragma unroll 2
             for (int r = slot; r < nb; r += 4) {
@@ -958,11 +967,11 @@ static int train_advance_inner(dr_model* m, int* kind, void** ptr, long long* co
             if (n_rm) {
                 unsigned blocks = std::max(1u, std::min<unsigned>(nblk(n_rm), 148u * 8u));
                 dr_loss_grad_kernel<<<blocks, 256, 0, st>>>(out_mb, ws->y + (size_t)b0 * T * Ml, ws->dy16, n_rm, m->cfg.quantiles[0],
-                                                             m->cfg.quantiles[1], m->cfg.quantiles[2], inv_n, acc);
+                                                             m->cfg.quantiles[1], m->cfg.quantiles[2], inv_n, acc, bm, T, Ml);   // dy time-major
                 DR_CUDA(m, cudaGetLastError());
                 m->launches += 1;
             }
-            // G-bar[(b,t)][k] = sum_{e,q} Abar[e][q][k] dy[b,t,e,q]: one fp32 GEMM [bm*T x 3M_loc] x [3M_loc x 2H]
+            // G-bar[(t,b)][k] = sum_{e,q} Abar[e][q][k] dy[(t,b),e,q]: one fp32 GEMM [T*bm x 3M_loc] x [3M_loc x 2H] (rows time-major)
             if (Ml) {
                 Gemm gg{ws->dy16, m->d_abar, ws->gbar16, (int)((size_t)bm * T), DR_2H, Ml * DR_Q,
                         (long)Ml * DR_Q, 1, DR_2H, 1, DR_2H, 1, 0, 0, 0, 0.0f};
