@@ -160,7 +160,7 @@ class QuantileRNN:
                 "training-mode forward (dropout + autograd, qrnn.py:43 / estimate.py:70-74) is served by "
                 "train_step(); call .eval() for inference")
         if _is_torch(input_seq) and input_seq.is_cuda:
-            return self._forward_torch(input_seq, borrow)
+            return self._forward_torch(input_seq, borrow, out)
         if self.world != 1:
             return self._forward_sharded_host(input_seq, out)
         x = np.ascontiguousarray(input_seq.detach().cpu().numpy() if _is_torch(input_seq) else input_seq,
@@ -249,7 +249,7 @@ class QuantileRNN:
                 return torch.as_tensor(_Buf(), device=dev)
         return _Pending()
 
-    def _forward_torch(self, x, borrow=False):
+    def _forward_torch(self, x, borrow=False, out=None):
         import torch
         if x.dtype != torch.float32 or x.dim() != 3 or x.shape[2] != self.input_size:
             raise ValueError(f"input_seq must be float32 [B,T,{self.input_size}]")
@@ -257,7 +257,11 @@ class QuantileRNN:
         B, T, _ = x.shape
         self._bind_stream()
         if self.world == 1:
-            out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
+            if out is None:
+                out = torch.empty((B, T, self.num_metrics, layout.Q), device=x.device, dtype=torch.float32)
+            elif (not _is_torch(out) or not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+                  or tuple(out.shape) != (B, T, self.num_metrics, layout.Q)):
+                raise ValueError("out must be a contiguous float32 CUDA tensor [B,T,M,Q]")
             _lib.check(self._h, self._lib.dr_forward_dev(self._h, x.data_ptr(), B, T, out.data_ptr()))
             return out
         from .sharding import sharded_forward
