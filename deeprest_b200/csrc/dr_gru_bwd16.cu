@@ -26,8 +26,6 @@ constexpr uint32_t kSmem = kOffBar + 128;
 constexpr uint32_t kColD = 0, kColA = 128;          // TMEM: D 128 fp32 columns, A = dgh as bf16 pairs (192 columns)
 enum BwBar { BW_W_LAND = 0, BW_A_READY, BW_D_FULL, BW_NUM };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
 struct Bwd16Args {
     const uint8_t* wimg;      // [M_loc][2][kWImg]
     uint8_t* gate;            // gate images, in: (r,z,n,q)  out: (da_r,da_z,da_n,dq)

@@ -136,12 +136,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
                  :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 
-// registers -> TMEM: this warp's 32 lanes x 4 consecutive 32-bit columns
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
-                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
-}
-
 // ---------------------------------------------------------------- descriptors
 // K-major, 128-byte swizzle canonical layout (cute UMMA::Layout_K_SW128_Atom):
 //   rows of 64 bf16 (128 B); 8-row groups of 1024 B (SBO); 16-byte chunk index ^= (row & 7).
