@@ -1,43 +1,47 @@
 """ORACLE-side runner of the reference's OWN CPU implementation (test / bench infrastructure, NOT product code).
 
-`/root/reference` does not exist on the GPU box, and reference sources are never committed.  `ensure_ref_copy()` — called
-by `__graft_entry__.build()` in the authoring container — copies the one module the hot path lives in
-(`resource-estimation/qrnn.py`) into `oracle/_ref/` (git-ignored, but shipped to the GPU box with the snapshot), so that
-`bench.py`'s `cpu_baseline` / `--impl reference` legs time the UNMODIFIED reference module (`kind: "reference"`).  When the
-copy is absent the torch port `oracle/qrnn_torch_cpu.py` stands in (`kind: "port"`).  Only `bench.py`'s CPU legs and tests
+`/root/reference` does not exist on the GPU box, and reference sources are never copied into this repository.
+`ensure_ref_copy()` — called by `__graft_entry__.build()` in the authoring container — byte-compiles the one module the hot
+path lives in (`resource-estimation/qrnn.py`, compiled where it lies) into `oracle/_ref/qrnn.pyc` (a build output:
+git-ignored, but shipped to the GPU box with the snapshot like the built `.so`), so that `bench.py`'s `cpu_baseline` /
+`--impl reference` legs time the UNMODIFIED reference module (`kind: "reference"`).  When the compiled module is absent the
+torch port `oracle/qrnn_torch_cpu.py` stands in (`kind: "port"`).  Only `bench.py`'s CPU legs and tests
 import this file.
 """
 from __future__ import annotations
 
+import importlib.machinery
 import importlib.util
 import os
-import shutil
+import py_compile
 
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SRC = "/root/reference/resource-estimation/qrnn.py"
-REF_DST = os.path.join(HERE, "_ref", "qrnn.py")
+REF_DST = os.path.join(HERE, "_ref", "qrnn.pyc")
 
 
 def ensure_ref_copy() -> bool:
-    """Copy the reference module next to the oracle (build step; no-op where /root/reference is absent)."""
+    """Byte-compile the reference module (from where it lies) into oracle/_ref/ — a build step; a no-op where
+    /root/reference is absent (the GPU box uses the prebuilt file)."""
     if os.path.exists(REF_SRC):
         os.makedirs(os.path.dirname(REF_DST), exist_ok=True)
-        if not os.path.exists(REF_DST) or open(REF_SRC, "rb").read() != open(REF_DST, "rb").read():
-            shutil.copyfile(REF_SRC, REF_DST)
+        if not os.path.exists(REF_DST) or os.path.getmtime(REF_DST) < os.path.getmtime(REF_SRC):
+            py_compile.compile(REF_SRC, cfile=REF_DST, doraise=True)
     return os.path.exists(REF_DST)
 
 
 def _import_ref():
-    spec = importlib.util.spec_from_file_location("deeprest_reference_qrnn", REF_DST)
+    loader = importlib.machinery.SourcelessFileLoader("deeprest_reference_qrnn", REF_DST)
+    spec = importlib.util.spec_from_loader("deeprest_reference_qrnn", loader)
     mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
+    loader.exec_module(mod)
     return mod
 
 
 class Runner:
-    """The reference estimator on the host CPU: `kind` is "reference" (the copied qrnn.py) or "port"."""
+    """The reference estimator on the host CPU: `kind` is "reference" (the byte-compiled reference qrnn.py) or "port"."""
 
     def __init__(self, blob, M, F, threads=None):
         import torch
@@ -58,7 +62,7 @@ class Runner:
 
     def describe(self):
         t = self.torch
-        what = ("the reference's own resource-estimation/qrnn.py (unmodified copy in oracle/_ref/)" if self.kind == "reference"
+        what = ("the reference's own resource-estimation/qrnn.py (byte-compiled, unmodified, in oracle/_ref/)" if self.kind == "reference"
                 else "reference algorithm restated on torch (oracle/qrnn_torch_cpu.py) incl. its O(M^2) stack/mean")
         return f"{what}, torch {t.__version__} CPU, {t.get_num_threads()} threads"
 
@@ -80,7 +84,7 @@ class Runner:
         other outputs, mean, concat and head (qrnn.py:46-54).  Used where all M heads would cost O(M^2) minutes."""
         t = self.torch
         if self.kind != "reference":
-            raise RuntimeError("forward_sampled needs the reference module (oracle/_ref/qrnn.py)")
+            raise RuntimeError("forward_sampled needs the reference module (oracle/_ref/qrnn.pyc)")
         m = self.model
         xs = t.from_numpy(np.ascontiguousarray(x))
         with t.no_grad():

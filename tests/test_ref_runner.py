@@ -31,7 +31,7 @@ def test_runner_forward_matches_oracle(runner):
 
 def test_sampled_heads_equal_the_full_forward(runner):
     if runner.kind != "reference":
-        pytest.skip("needs the reference module (oracle/_ref/qrnn.py)")
+        pytest.skip("needs the reference module (oracle/_ref/qrnn.pyc)")
     x = synth.windows(4, B, T, F, "diurnal")
     full = runner.forward(x)
     ids = [0, 3, 5]
