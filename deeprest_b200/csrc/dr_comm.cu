@@ -22,7 +22,8 @@
 
 namespace {
 
-constexpr int kMaxWorld = 8, kMaxChunks = 64, kChunk = 256, kRing = 256;
+constexpr int kMaxWorld = 8, kMaxChunks = 64, kChunk = 256;
+constexpr int kRing = 4096;      // epoch staging slots: far more forwards than the launch queues can hold ahead of the GPU
 typedef CUresult (*PFN_wait32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
 // One arena per device and process, kept until the process exits: a later model on the same device (e.g. a second estimator
@@ -82,7 +83,7 @@ void layout_arena(DrComm* c, int M_total) {
 
 }  // namespace
 
-// unmap the peers' arenas (after this rank's queued work has drained)
+// drain this handle's queued sharded work
 static void comm_detach(DrComm* c) {
     cudaStream_t sts[] = {c->cs, c->ss, c->xs, c->os, c->ds};
     for (cudaStream_t s : sts) if (s) cudaStreamSynchronize(s);

@@ -56,11 +56,14 @@ class QuantileRNN:
         self.training = True                     # nn.Module default
         self._pg = process_group
         self._engine, self._peer = engine, None
-        # sharded runs: let the head kernel store into every rank's forecast tensor (peer memory) instead of NCCL
-        # all-gather + interleave.  Measured: +7 % at 2 GPUs, but at 8 GPUs its 64-byte peer stores reach only about a
-        # third of NCCL's all-gather bandwidth (49.0 vs 37.1 ms/step, profiles/r01_run_r / r01_run_l) -> default off there.
-        # "kernel": K2 stores to the peers; "copy": strided 2-D peer copies by the DMA engines after K2; "nccl": all_gather
-        # + interleave kernel; "auto": kernel for world <= 2, copy otherwise.
+        # sharded runs (world > 1), how the partial sums S and the forecast columns cross the ranks:
+        #   "dma"   : the library's own exchange behind ONE C-ABI call (csrc/dr_comm.cu): one recurrence launch, copy engines
+        #             move S and the forecasts, no NCCL and no SM-resident collective — round-2 default
+        #   "copy"  : round-1 path: NCCL all-reduce of S per chunk, forecasts by strided 2-D peer copies after the head kernel
+        #   "kernel": as "copy", but the head kernel stores straight into the peers' tensors (good at 2 GPUs, slow at 8:
+        #             49.0 vs 37.1 ms/step, profiles/r01_run_r / r01_run_l)
+        #   "nccl"  : NCCL all-reduce + all-gather + interleave kernel
+        #   "auto"  : "dma" where the tcgen05 engine runs (input_size <= 64), else "copy"
         self.gather_mode = "auto"
         if process_group is not None or (world or 1) > 1:
             import torch.distributed as dist
@@ -95,7 +98,8 @@ class QuantileRNN:
     # ---- lifecycle -------------------------------------------------------------------
     def close(self):
         """Frees the handle.  For an expert-sharded handle that has run the library's exchange this is COLLECTIVE: every rank
-        unmaps its peers' arenas, the ranks synchronise, then the memory is freed (CUDA IPC teardown rule)."""
+        drains its own sharded forwards, the ranks synchronise (no peer is still copying into this rank), then the handle
+        goes away.  The exchange arena itself is process-wide and stays (include/deeprest_b200.h, dr_comm_init)."""
         if getattr(self, "_h", None) and self._h.value and getattr(self, "_comm_shape", None):
             self._lib.dr_comm_detach(self._h)
             self._comm_shape = None
@@ -189,7 +193,7 @@ class QuantileRNN:
         """Collective: size this rank's arena for calls up to [max_windows, seq_len] and map the peers' arenas (CUDA IPC
         handles exchanged through the process group — the only thing torch.distributed does for the forward)."""
         import torch.distributed as dist
-        if getattr(self, "_comm_shape", None):           # re-sizing: nobody may still map the arena that is about to be freed
+        if getattr(self, "_comm_shape", None):           # re-sizing: no peer may still be copying into this rank
             self._lib.dr_comm_detach(self._h)
             dist.barrier(group=self._pg)
         handle = (C.c_ubyte * 64)()

@@ -147,15 +147,23 @@ int  dr_interleave_dev   (dr_model* m, const float* gathered_dev, int32_t B, int
  * its peers map; the recurrence kernel runs as one launch and flags finished 256-window tiles, copy engines move each tile's
  * partial S to the peers, the head kernel adds the partials in rank order (bit-identical on every rank) and the forecast
  * columns are placed into every rank's stacked tensor [B,T,M,Q] (qrnn.py:55) by strided 2-D peer copies.
- *   dr_comm_init   : allocate this rank's arena for calls up to [Bmax, T]; returns its CUDA IPC handle (64 bytes; for one
+ *   dr_comm_init   : size this rank's arena for calls up to [Bmax, T]; returns its CUDA IPC handle (64 bytes; for one
  *                    process per GPU) and its device pointer (for several handles inside one process).  Collective in the
  *                    sense that every rank must have returned from it before any rank calls dr_comm_attach.
+ *                    The arena is ONE allocation per (process, device), made by the first dr_comm_init on that device and
+ *                    kept until the process exits (CUDA IPC rule: an exported allocation must not be freed while an importer
+ *                    may still map it).  Later handles on the same device reuse it and the peer mappings; it must fit the
+ *                    largest of them — create that handle first or set DR_COMM_ARENA_GB — else DR_ENOMEM.
  *   dr_comm_attach : map the peers' arenas — `ipc_handles` = world x 64 bytes in rank order (own entry ignored), or
- *                    `arena_ptrs` = world device pointers of the same process (peer access is enabled here).
- *   dr_comm_detach : unmap the peers' arenas.  Teardown order across ranks (CUDA IPC rule: an exported allocation must not be
- *                    freed while an importer still maps it): every rank detaches, the host synchronises the ranks, then
- *                    every rank calls dr_destroy (or dr_comm_init again).  dr_destroy detaches by itself, which is enough for
- *                    several handles inside one process.
+ *                    `arena_ptrs` = world device pointers of the same process (peer access is enabled here).  Peers mapped by
+ *                    an earlier handle of this process are reused.
+ *   dr_comm_detach : drain this handle's sharded forwards (all of its internal streams).  Teardown order across ranks: every
+ *                    rank detaches, the host synchronises the ranks, then every rank calls dr_destroy (or dr_comm_init
+ *                    again) — so that no peer is still copying into this rank when its handle goes away.  dr_destroy
+ *                    detaches by itself, which is enough for several handles inside one process.
+ *   Handles that share a device share the arena: drain one handle's sharded forwards (dr_comm_detach or a stream
+ *   synchronise on every rank) before another handle on that device issues one.  A sharded forward that fails part-way on one
+ *   rank (any code other than DR_OK) leaves its peers waiting for signals that will not come: tear the group down.
  *   dr_forward_sharded_dev : x_dev [B,T,F] (replicated) -> *out_dev = the stacked forecasts [B,T,M,Q] in this rank's arena.
  *                    Asynchronous on the handle's stream (dr_set_stream).  The tensor stays valid until the second-next
  *                    sharded forward on this handle (two tensors alternate); copy it if it must live longer.
